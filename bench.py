@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- G body-body interactions/s of the brute-force step (force + fused integrator).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n N] [--precision 32|64]
+
+One "step" = one pass of the hot path over all N bodies: all N(N-1) ordered interactions plus
+the per-body update (v += F/m dt; x += v dt).  Workload at every GPU count = BASELINE.json
+configs[4]: 3D, N = 1,048,576 bodies in a uniform cube (strong scaling: N is fixed, targets are
+sharded over the GPUs).  For --gpus N > 1 launch under torchrun, one rank per GPU.
+
+Product arm: libnb200.so through its C ABI (include/nb200.h).  `value` is timed with CUDA
+events recorded by the library on its compute stream around each step, inputs resident in HBM,
+MAX over ranks; `e2e` goes through the public host-buffer API (upload from pinned host memory +
+step + download, every step) by wall clock.  Reference arm (--impl reference): the reference's
+own brute-force code compiled unmodified (oracle/_ref) -- or the oracle port when that library
+is absent -- on this box's host cores, on a bounded sample of the same workload.
+
+Nothing here imports oracle/ on the product path: only `cpu_baseline` and `--impl reference` do.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+N_DEFAULT = 1 << 20
+DIM = 3
+DT = 1e-3
+SEED = 42 + 5
+FLOPS_PER_INTERACTION = 20          # north_star / GPU-Gems convention
+SM_LANES_FP32 = 128                 # FP32 FMA lanes per SM (sm_100)
+CPU_SAMPLE_N = 16384                # bounded CPU sample of the same distribution
+
+
+def interactions(n: int) -> float:
+    return float(n) * float(n - 1)
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------- CPU legs
+def cpu_reference_leg(n_sample: int, repeats: int = 1) -> dict:
+    """Time the reference's own brute-force variants (oracle/_ref; else the oracle port) on this
+    box's host cores, one force evaluation each (the reference's convention, utils.h:87-104)."""
+    oracle = entry.load_oracle()
+    pkg = entry.load_package()
+    bodies = pkg.generators.uniform_cube(N_DEFAULT, DIM, seed=SEED)[:n_sample].copy()
+    inter = interactions(n_sample)
+    cores = os.cpu_count() or 1
+    out = {"unit": "G interactions/s", "cores": cores,
+           "sample": f"first {n_sample} bodies of the 3D uniform-cube workload, one force evaluation per variant"}
+    if oracle.have_ref():
+        out["kind"] = "reference"
+        thr = oracle.ref_threads()
+        out["threads"] = {"omp": thr["omp"], "parlay": thr["parlay"]}
+        variants = {}
+        for v in ("omp_2", "omp_1", "parlay_1", "parlay_2"):
+            best = min(oracle.ref_forces(bodies, v, want_forces=False)[1] for _ in range(repeats))
+            variants[v] = round(inter / best / 1e9, 4)
+        out["variants"] = variants
+        out["value"] = max(variants.values())
+        out["best_variant"] = max(variants, key=variants.get)
+        out["cores"] = max(thr["omp"], thr["parlay"])
+    else:
+        out["kind"] = "port"
+        t0 = time.perf_counter()
+        oracle.forces(bodies)
+        out["value"] = round(inter / (time.perf_counter() - t0) / 1e9, 4)
+        out["cores"] = oracle.num_threads()
+    return out
+
+
+def run_reference_arm(args) -> None:
+    """--impl reference: the reference's CPU implementation of the step on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    oracle = entry.load_oracle()
+    pkg = entry.load_package()
+    n_s = min(args.n, CPU_SAMPLE_N)
+    bodies = pkg.generators.uniform_cube(args.n, DIM, seed=SEED)[:n_s].copy()
+    use_ref = oracle.have_ref()
+
+    def one_step(b):
+        return oracle.ref_simulate(b, DT, 1, "omp_2") if use_ref else oracle.simulate(b, DT, 1)
+
+    for _ in range(args.warmup):
+        bodies = one_step(bodies)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bodies = one_step(bodies)
+    dt = time.perf_counter() - t0
+    val = interactions(n_s) * args.steps / dt / 1e9
+    cores = (oracle.ref_threads()["omp"] if use_ref else oracle.num_threads())
+    line = {
+        "impl": "reference", "metric": "G body-body interactions/s (brute-force step, 3D)", "value": round(val, 4),
+        "unit": "G interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"c5: brute-force 3D uniform cube, N={args.n} (reference arm: CPU sample of {n_s} bodies)",
+                   "n": args.n, "dim": DIM, "dt": DT},
+        "cpu_baseline": {"value": round(val, 4), "unit": "G interactions/s", "cores": cores,
+                         "kind": "reference" if use_ref else "port",
+                         "sample": f"{args.steps} steps of brute_force_omp_n_body_2 + update_body_* on the first "
+                                   f"{n_s} bodies of the workload (methods.cpp:98-136,426-450), all host threads"},
+        "e2e": {"value": round(val, 4), "unit": "G interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------- product arm
+def run_product_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    pkg = entry.load_package()
+    from importlib import import_module
+    D = import_module(pkg.__name__ + ".distributed")
+
+    rank, world, local = D.env_rank_world()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, prec = args.n, args.precision
+    bodies = pkg.generators.uniform_cube(n, DIM, seed=SEED)
+    if world > 1:
+        ctx = D.create_rank_context(pkg, DIM, n, prec, device=local)
+    else:
+        ctx = pkg.NBodyCuda(DIM, n, prec)
+    for kv in args.opt or []:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
+    ctx.upload(bodies)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
+
+    def flush_l2():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up steps, then EXACTLY K steps, L2 flushed between them
+    for _ in range(args.warmup):
+        ctx.step(DT, 1)
+    barrier()
+    l0 = ctx.launch_count
+    step_ms = []
+    sampler = ClockSampler(local)
+    with sampler:
+        barrier()
+        wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush_l2()
+            ctx.step(DT, 1)
+            step_ms.append(ctx.last_elapsed_ms)
+        barrier()
+        wall = time.perf_counter() - wall0
+    launches = ctx.launch_count - l0
+    dev_ms = max_over_ranks(sum(step_ms))
+    value = interactions(n) * args.steps / (dev_ms * 1e-3) / 1e9
+    clocks = sampler.summary()
+    plan = ctx.plan
+
+    # ---- the same K steps as ONE pipelined call (all-gather of step k+1 hidden behind pass A)
+    barrier()
+    ctx.step(DT, args.steps)
+    pipe_ms = max_over_ranks(ctx.last_elapsed_ms)
+    pipelined = interactions(n) * args.steps / (pipe_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer API: pinned host -> device, step, device -> host
+    host = torch.from_numpy(bodies.copy()).pin_memory()
+    host_np = host.numpy()
+    lo, hi = ctx.shard_range()
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.upload(host_np)
+        ctx.step(DT, 1)
+        ctx.download(host_np)
+        if world > 1:                       # every rank needs all positions for the next upload
+            full = D.assemble_rows(host_np, lo, hi)
+            host_np[:] = full
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_val = interactions(n) * e2e_steps / e2e_s / 1e9
+    h2d = n * (2 * DIM + 1) * 8
+    d2h = (hi - lo) * 2 * DIM * 8
+
+    # ---- FP64 flavour of the same step (the reference's own precision), short
+    fp64 = None
+    if prec == 32 and not args.no_fp64:
+        ctx.close()
+        ctx = D.create_rank_context(pkg, DIM, n, pkg.NB200_FP64, device=local) if world > 1 else pkg.NBodyCuda(DIM, n, pkg.NB200_FP64)
+        ctx.upload(bodies)
+        ctx.step(DT, 1)
+        barrier()
+        ctx.step(DT, 2)
+        ms64 = max_over_ranks(ctx.last_elapsed_ms)
+        v64 = interactions(n) * 2 / (ms64 * 1e-3) / 1e9
+        fp64 = {"value": round(v64, 2), "unit": "G interactions/s", "ms_per_step": round(ms64 / 2, 3), "steps": 2,
+                "roofline_frac_fp64": round(v64 * 1e9 * FLOPS_PER_INTERACTION / (148 * 64 * 2 * 1.965e9), 4)}
+    ctx.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    props = torch.cuda.get_device_properties(local)
+    sms = props.multi_processor_count
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+    lanes = SM_LANES_FP32 if prec == 32 else 64
+    peak_tflops = sms * lanes * 2 * sm_max * 1e6 / 1e12 * world
+    achieved_tflops = value * 1e9 * FLOPS_PER_INTERACTION / 1e12
+    roofline = {
+        "bound": "fp32_fma_pipe" if prec == 32 else "fp64_pipe",
+        "achieved": round(achieved_tflops, 2), "peak": round(peak_tflops, 2), "unit": "TFLOP/s",
+        "frac": round(achieved_tflops / peak_tflops, 4),
+        "peak_source": f"{sms} SMs x {lanes} FMA lanes x 2 x {sm_max:.0f} MHz x {world} GPU(s); MEASURED_PEAKS.json has only "
+                       "HBM and bf16-tensor peaks, neither bounds this kernel (20 flops/interaction convention)",
+        "frac_at_observed_clock": (round(achieved_tflops / (peak_tflops * clocks["sm_mhz"] / sm_max), 4)
+                                   if clocks.get("sm_mhz") else None),
+        "fma_pipe_lane_ops_per_interaction": 11,
+        "traffic": None,
+        "hbm_algorithmic_bytes_per_step": n * (16 if prec == 32 else 32) + n * (2 * DIM * 8 * 2 + 8 + 3 * 8 * 2),
+    }
+    line = {
+        "metric": "G body-body interactions/s (brute-force step, 3D)", "value": round(value, 2),
+        "unit": "G interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32" if prec == 32 else "f64", "data": "synthetic",
+        "config": {"workload": f"c5: brute-force 3D uniform cube, N={n}, fused force+integrate step, dt={DT}",
+                   "n": n, "dim": DIM, "precision": prec,
+                   "parallelism": f"targets sharded over {world} GPU(s), per-step position all-gather",
+                   "l2": "flushed between timed steps (256 MiB write)", "plan": plan},
+        "pipelined": {"value": round(pipelined, 2), "ms_per_step": round(pipe_ms / args.steps, 3),
+                      "note": "same K steps in one nb200_step call, no L2 flush, all-gather overlapped"},
+        "wall_s_timed_region": round(wall, 3),
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_val, 2), "unit": "G interactions/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if fp64:
+        line["fp64"] = fp64
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_reference_leg(min(n, CPU_SAMPLE_N))
+    if world > 1:
+        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nb200", choices=["nb200", "reference"])
+    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    ap.add_argument("--opt", action="append", help="libnb200 option key=value (e.g. variant=1)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fp64", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "nb200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_product_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,130 @@
+/*
+ * nb200.h -- C ABI of libnb200.so: the B200-native (sm_100a) brute-force N-body path.
+ *
+ * This is the drop-in boundary for ONE hot path of mathaiml5/NBody-simulation-parallel
+ * (paths below are relative to /root/reference/nbody-sim-new):
+ *
+ *   nb200_forces        replaces  brute_force_seq_n_body<D>       methods.h:30-31  methods.cpp:7-42
+ *                                 brute_force_omp_n_body_1<D>     methods.h:33-34  methods.cpp:45-95
+ *                                 brute_force_omp_n_body_2<D>     methods.h:36-37  methods.cpp:98-136
+ *                                 brute_force_parlay_n_body_1<D>  methods.h:39-40  methods.cpp:139-186
+ *                                 brute_force_parlay_n_body_2<D>  methods.h:42-43  methods.cpp:189-224
+ *   nb200_step          replaces  the loop {force; update_body_velocities<D>; update_body_positions<D>}
+ *                                 methods.h:85-91  methods.cpp:426-450   (semi-implicit Euler)
+ *   nb200_upload_aos /  take and return the reference's own AoS std::vector<Body<D>> bytes
+ *   nb200_download_aos            body.h:7-19  (stride 40 B for D=2, 56 B for D=3), vector.h:9-12
+ *   nb200_accuracy_pct  replaces  compute_accuracy_omp<D>         utils.h:170-219
+ *
+ * Semantics kept exactly as the reference codes them: F_i = -G m_i sum_j m_j (p_j - p_i) / r^4
+ * (methods.cpp:21-37), pairs with r^2 < cutoff DROPPED (methods.cpp:24; the reference hard-codes
+ * 1e-10), forces (not accelerations) returned in body order as D doubles per body, G and the
+ * cut-off passed at run time (the reference: utils.h:21, G = 4.471e-21).
+ *
+ * Plain pointers and sizes only; no exceptions cross this boundary; every entry point returns
+ * 0 on success or a negative NB200_E* code, with text from nb200_last_error().  There is no CPU
+ * fallback: without a usable sm_100 device every compute entry point fails with NB200_ECUDA.
+ *
+ * The C++ adapter with the reference's template signatures is
+ * nbody-simulation-parallel_b200/host/methods_cuda.h; INTEGRATION.md shows the binding.
+ */
+#ifndef NB200_H
+#define NB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nb200_ctx nb200_ctx;
+
+/* precision of the PAIR arithmetic */
+#define NB200_FP64 64 /* double throughout: <= 1e-12 per-body relative force error vs the reference */
+#define NB200_FP32 32 /* packed-FP32 pair math, FP64 accumulation/state/integration: <= 1e-5 */
+
+#define NB200_OK 0
+#define NB200_EINVAL (-1) /* bad argument */
+#define NB200_ECUDA (-2)  /* CUDA runtime error / no device */
+#define NB200_ENCCL (-3)  /* NCCL error or NCCL not loadable */
+#define NB200_ESTATE (-4) /* call sequence error (e.g. step before upload) */
+#define NB200_ENOMEM (-5)
+
+#define NB200_UNIQUE_ID_BYTES 128
+
+/* ---- lifetime --------------------------------------------------------------------------- */
+
+/* Single-process context over `ngpus` devices (0..ngpus-1, or the list in env NB200_DEVICES):
+ * targets are sharded by contiguous index range, one NCCL communicator per device
+ * (ncclCommInitAll) when ngpus > 1.  dim = 2 or 3; n = number of bodies. */
+int nb200_create(nb200_ctx** out, int dim, size_t n, int precision, int ngpus);
+
+/* One-process-per-GPU context (torchrun style): this process owns shard `rank` of `world` on
+ * CUDA device `device`.  unique_id = NB200_UNIQUE_ID_BYTES bytes from nb200_get_unique_id() on
+ * rank 0, broadcast by the caller (any transport); may be NULL when world == 1.  NULL with
+ * world > 1 builds a DETACHED shard without a communicator (test hook): nb200_forces works,
+ * nb200_step is limited to nsteps == 1 and the caller re-uploads before the next step. */
+int nb200_create_rank(nb200_ctx** out, int dim, size_t n, int precision, int device, int rank,
+                      int world, const void* unique_id);
+int nb200_get_unique_id(void* unique_id_out);
+
+void nb200_destroy(nb200_ctx* ctx);
+
+/* ---- data ------------------------------------------------------------------------------- */
+
+/* bodies = n records of the reference's Body<D>: position[D], velocity[D], mass (doubles);
+ * stride in bytes (40 for D=2, 56 for D=3, or larger).  Every rank passes ALL n bodies. */
+int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride);
+
+/* Writes position and velocity (mass untouched) of the bodies this context owns back into an
+ * AoS array of ALL n bodies: every body for nb200_create contexts, rows [lo,hi) of
+ * nb200_shard_range for nb200_create_rank contexts. */
+int nb200_download_aos(nb200_ctx* ctx, void* bodies, size_t stride);
+
+/* Owned target range [lo, hi) in body indices. */
+int nb200_shard_range(const nb200_ctx* ctx, size_t* lo, size_t* hi);
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+
+/* One force evaluation at the uploaded positions.  forces_out = n*D doubles (Vector<D> layout,
+ * body order); rank contexts fill rows [lo,hi) only.  Does not change the state. */
+int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out);
+
+/* nsteps of: F = brute force; v += (F/m) dt; x += v dt  -- entirely on the device(s), integrator
+ * fused into the force kernel's epilogue, one position all-gather per step when sharded. */
+int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps);
+
+/* Kinetic and potential energy of the reference's own law (U = sum_{i<j} G m_i m_j / (2 r^2),
+ * pairs under the cut-off excluded).  Rank contexts return their shard's partial sums. */
+int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, double* potential);
+
+/* utils.h:170-219 on the host-resident arrays (n*D doubles each): percentage of bodies whose
+ * every component is within 1 % of the reference (absolute 1e-9 test when |ref| < 1e-20). */
+int nb200_accuracy_pct(nb200_ctx* ctx, const double* forces, const double* reference, double* pct);
+
+/* ---- introspection / measurement --------------------------------------------------------- */
+
+/* Device time (CUDA events on the launching stream, max over this context's devices) of the
+ * kernels of the last nb200_forces / nb200_step call, in milliseconds. */
+int nb200_last_elapsed_ms(const nb200_ctx* ctx, double* ms);
+
+/* Kernel launches issued by this context since creation (our own kernels only). */
+long long nb200_launch_count(const nb200_ctx* ctx);
+
+/* Tuning knobs (all optional; 0 restores the heuristic):
+ *   "variant"     index into the compiled (targets/thread, j-split, block) table, -1 = auto
+ *   "seg_tiles"   source tiles (of 256 bodies) per work unit
+ *   "grid_mult"   persistent CTAs = grid_mult * (SMs * occupancy) / 16  (16 = exactly resident)
+ *   "overlap"     1 = split each step into local/remote passes around the all-gather (default)
+ * Returns NB200_EINVAL for an unknown key. */
+int nb200_set_option(nb200_ctx* ctx, const char* key, long value);
+
+/* Human-readable one-line description of the launch plan of the last call (for logs). */
+const char* nb200_plan(const nb200_ctx* ctx);
+
+const char* nb200_last_error(const nb200_ctx* ctx); /* ctx may be NULL: last create() error */
+const char* nb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NB200_H */

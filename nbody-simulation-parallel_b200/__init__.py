@@ -1,0 +1,180 @@
+"""nbody-simulation-parallel_b200 -- B200-native brute-force N-body path (Python host mirror).
+
+The product is ``lib/libnb200.so`` (hand-written sm_100a kernels behind the C ABI of
+``include/nb200.h``) and the C++ adapter ``host/methods_cuda.h`` that gives it the reference's
+``methods.h`` signatures.  This module is the thin ctypes mirror used by tests and ``bench.py``;
+function names follow the reference's entry points (methods.h:29-43, :85-91):
+
+    brute_force_cuda_n_body(bodies)              -> forces        (cf. brute_force_omp_n_body_2<D>)
+    brute_force_cuda_simulate(bodies, dt, steps) -> bodies after  (force + update_body_* loop)
+
+``bodies`` is the reference's AoS ``Body<D>`` as a float64 array (n, 2*D+1).  The directory name
+is not a Python identifier; load it with ``__graft_entry__.load_package()``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import generators
+from ._lib import NB200_FP32, NB200_FP64
+
+#: the reference's compile-time constants (utils.h:21; methods.cpp:24)
+G_REF = 4.471e-21
+CUTOFF_REF = 1e-10
+
+
+class NB200Error(RuntimeError):
+    pass
+
+
+def _dim_of(bodies: np.ndarray) -> int:
+    if bodies.ndim != 2 or bodies.shape[1] not in (5, 7):
+        raise ValueError("bodies must be (n, 5) for 2D or (n, 7) for 3D (Body<D>: pos, vel, mass)")
+    return (bodies.shape[1] - 1) // 2
+
+
+class NBodyCuda:
+    """One libnb200 context (``nb200_ctx``).
+
+    ``ngpus`` > 1 drives several GPUs from this process; ``rank``/``world``/``unique_id`` build
+    the one-process-per-GPU flavour used under torchrun (see ``distributed.py``).
+    """
+
+    def __init__(self, dim: int, n: int, precision: int = NB200_FP64, ngpus: int = 1, *, device: int | None = None,
+                 rank: int | None = None, world: int | None = None, unique_id: bytes | None = None):
+        self._lib = _lib.load()
+        self.dim, self.n, self.precision = dim, n, precision
+        self._h = ctypes.c_void_p()
+        if rank is None:
+            rc = self._lib.nb200_create(ctypes.byref(self._h), dim, n, precision, ngpus)
+        else:
+            buf = ctypes.create_string_buffer(unique_id, _lib.UNIQUE_ID_BYTES) if unique_id else None
+            rc = self._lib.nb200_create_rank(ctypes.byref(self._h), dim, n, precision,
+                                             0 if device is None else device, rank, world or 1, buf)
+        if rc != 0:
+            msg = self._lib.nb200_last_error(None)
+            self._h = ctypes.c_void_p()
+            raise NB200Error(f"nb200 create failed ({rc}): {msg.decode() if msg else ''}")
+
+    # -- plumbing
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self._lib.nb200_last_error(self._h)
+            raise NB200Error(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.nb200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        self._check(self._lib.nb200_set_option(self._h, key.encode(), int(value)), f"set_option({key})")
+
+    # -- data
+    def upload(self, bodies: np.ndarray):
+        b = np.ascontiguousarray(bodies, dtype=np.float64)
+        if b.shape != (self.n, 2 * self.dim + 1):
+            raise ValueError(f"expected bodies of shape {(self.n, 2 * self.dim + 1)}, got {b.shape}")
+        self._check(self._lib.nb200_upload_aos(self._h, b.ctypes.data, b.strides[0] if self.n else 8 * (2 * self.dim + 1)),
+                    "upload")
+        self._stride = b.strides[0] if self.n else 8 * (2 * self.dim + 1)
+
+    def download(self, into: np.ndarray) -> np.ndarray:
+        """Overwrite position and velocity of the owned rows of ``into`` (masses untouched)."""
+        if into.dtype != np.float64 or not into.flags.c_contiguous or into.shape != (self.n, 2 * self.dim + 1):
+            raise ValueError("download target must be a C-contiguous float64 (n, 2D+1) array")
+        self._check(self._lib.nb200_download_aos(self._h, into.ctypes.data, self._stride), "download")
+        return into
+
+    def shard_range(self) -> tuple[int, int]:
+        lo, hi = ctypes.c_size_t(), ctypes.c_size_t()
+        self._check(self._lib.nb200_shard_range(self._h, ctypes.byref(lo), ctypes.byref(hi)), "shard_range")
+        return lo.value, hi.value
+
+    # -- the hot path
+    def forces(self, G: float = G_REF, cutoff: float = CUTOFF_REF, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.zeros((self.n, self.dim))
+        self._check(self._lib.nb200_forces(self._h, G, cutoff, out.ctypes.data_as(_lib._dp)), "forces")
+        return out
+
+    def step(self, dt: float, nsteps: int = 1, G: float = G_REF, cutoff: float = CUTOFF_REF):
+        self._check(self._lib.nb200_step(self._h, G, cutoff, dt, nsteps), "step")
+
+    def energy(self, G: float = G_REF, cutoff: float = CUTOFF_REF) -> tuple[float, float]:
+        ke, pe = ctypes.c_double(), ctypes.c_double()
+        self._check(self._lib.nb200_energy(self._h, G, cutoff, ctypes.byref(ke), ctypes.byref(pe)), "energy")
+        return ke.value, pe.value
+
+    def accuracy_pct(self, forces: np.ndarray, reference: np.ndarray) -> float:
+        f = np.ascontiguousarray(forces, dtype=np.float64)
+        r = np.ascontiguousarray(reference, dtype=np.float64)
+        pct = ctypes.c_double()
+        self._check(self._lib.nb200_accuracy_pct(self._h, f.ctypes.data_as(_lib._dp), r.ctypes.data_as(_lib._dp),
+                                                 ctypes.byref(pct)), "accuracy_pct")
+        return pct.value
+
+    # -- measurement
+    @property
+    def last_elapsed_ms(self) -> float:
+        ms = ctypes.c_double()
+        self._check(self._lib.nb200_last_elapsed_ms(self._h, ctypes.byref(ms)), "last_elapsed_ms")
+        return ms.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.nb200_launch_count(self._h))
+
+    @property
+    def plan(self) -> str:
+        p = self._lib.nb200_plan(self._h)
+        return p.decode() if p else ""
+
+
+def brute_force_cuda_n_body(bodies: np.ndarray, precision: int = NB200_FP64, ngpus: int = 1, G: float = G_REF,
+                            cutoff: float = CUTOFF_REF, options: dict | None = None) -> np.ndarray:
+    """Forces on every body, (n, D) float64 in body order -- the ``BruteForce_CUDA`` method beside
+    ``brute_force_{seq,omp_1,omp_2,parlay_1,parlay_2}_n_body`` (methods.h:29-43).  Host buffers in,
+    host buffers out (the timing convention of ``safely_execute``, utils.h:87-104)."""
+    b = np.ascontiguousarray(bodies, dtype=np.float64)
+    dim = _dim_of(b)
+    with NBodyCuda(dim, b.shape[0], precision, ngpus) as ctx:
+        for k, v in (options or {}).items():
+            ctx.set_option(k, v)
+        ctx.upload(b)
+        return ctx.forces(G, cutoff)
+
+
+def brute_force_cuda_simulate(bodies: np.ndarray, dt: float, steps: int, precision: int = NB200_FP64,
+                              ngpus: int = 1, G: float = G_REF, cutoff: float = CUTOFF_REF,
+                              options: dict | None = None) -> np.ndarray:
+    """``steps`` iterations of {brute force; update_body_velocities; update_body_positions}
+    (methods.cpp:426-450) on the device(s); returns the advanced AoS bodies."""
+    b = np.array(bodies, dtype=np.float64, order="C", copy=True)
+    dim = _dim_of(b)
+    with NBodyCuda(dim, b.shape[0], precision, ngpus) as ctx:
+        for k, v in (options or {}).items():
+            ctx.set_option(k, v)
+        ctx.upload(b)
+        ctx.step(dt, steps, G, cutoff)
+        ctx.download(b)
+    return b
+
+
+__all__ = ["NBodyCuda", "NB200Error", "NB200_FP32", "NB200_FP64", "G_REF", "CUTOFF_REF",
+           "brute_force_cuda_n_body", "brute_force_cuda_simulate", "generators"]

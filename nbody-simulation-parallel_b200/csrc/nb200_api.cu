@@ -1,0 +1,806 @@
+// nb200_api.cu -- the extern "C" layer of libnb200.so (see include/nb200.h for the contract and
+// the reference file:line each entry point replaces).
+//
+// One nb200_ctx owns one Shard per device it drives: G shards in a single-process context
+// (nb200_create, ncclCommInitAll), exactly one in a rank context (nb200_create_rank,
+// ncclCommInitRank; one process per GPU under torchrun).  A shard owns a contiguous range of
+// TARGET tiles, their FP64 master state, and a full double-buffered copy of the tile-planar
+// SOURCES of all bodies.  Per step and shard:
+//     compute stream:  pass A (sources = own shard, already local)
+//                      wait(all-gather of this step's positions)
+//                      pass B (sources = the other shards) + fused integrator epilogue
+//                         -> writes the own rows of the NEXT source buffer
+//     comm stream:     wait(pass B) ; in-place ncclAllGather of the next buffer
+// so the all-gather of step k+1 hides behind pass A of step k+1.  NCCL is dlopen'ed on first
+// multi-GPU use (no link-time dependency; a 1-GPU context never touches it).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/nb200.h"
+#include "nb_aux.cuh"
+#include "nb_force.cuh"
+
+#define NB200_VERSION_STR "nb200 0.1 (sm_100a)"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------- NCCL (lazy)
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("NB200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            if (!nm || !*nm) continue;
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) {
+            api.error = std::string("cannot dlopen NCCL: ") + (dlerror() ? dlerror() : "?");
+            return;
+        }
+#define NB_SYM(field, name)                                                    \
+    *(void**)(&api.field) = dlsym(api.handle, name);                           \
+    if (!api.field) { api.error = std::string("NCCL symbol missing: ") + name; return; }
+        NB_SYM(GetUniqueId, "ncclGetUniqueId")
+        NB_SYM(CommInitRank, "ncclCommInitRank")
+        NB_SYM(CommInitAll, "ncclCommInitAll")
+        NB_SYM(CommDestroy, "ncclCommDestroy")
+        NB_SYM(AllGather, "ncclAllGather")
+        NB_SYM(GroupStart, "ncclGroupStart")
+        NB_SYM(GroupEnd, "ncclGroupEnd")
+        NB_SYM(GetErrorString, "ncclGetErrorString")
+#undef NB_SYM
+    });
+    return &api;
+}
+
+// ------------------------------------------------------------------------------- kernel table
+struct Variant {
+    int ti, js, block;
+    int itile() const { return block / js * ti; }
+};
+// index = "variant" option.  Large i-tiles first (the auto-planner prefers the largest that still
+// yields enough work units).
+const Variant kVariants[] = {
+    {4, 1, 256},   // 0: 1024 targets per i-tile
+    {2, 1, 256},   // 1:  512
+    {4, 4, 256},   // 2:  256
+    {2, 4, 128},   // 3:   64
+    {2, 8, 128},   // 4:   32
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+typedef void (*ForceKernel)(const NbForceParams);
+
+template <int D, bool F64> ForceKernel kernel_for(int v) {
+    switch (v) {
+        case 0: return nb_force_kernel<D, F64, 4, 1, 256>;
+        case 1: return nb_force_kernel<D, F64, 2, 1, 256>;
+        case 2: return nb_force_kernel<D, F64, 4, 4, 256>;
+        case 3: return nb_force_kernel<D, F64, 2, 4, 128>;
+        default: return nb_force_kernel<D, F64, 2, 8, 128>;
+    }
+}
+ForceKernel pick_kernel(int dim, bool f64, int v) {
+    if (dim == 3) return f64 ? kernel_for<3, true>(v) : kernel_for<3, false>(v);
+    return f64 ? kernel_for<2, true>(v) : kernel_for<2, false>(v);
+}
+
+size_t smem_bytes(int dim, bool f64) {
+    const size_t tile = (size_t)NB_TILE * (dim + 1) * (f64 ? 8 : 4);
+    return NB_STAGES * tile + 2 * NB_STAGES * sizeof(uint64_t) + 16;
+}
+
+// ------------------------------------------------------------------------------- state
+struct Shard {
+    int device = 0;
+    int rank = 0;
+    long long tile_lo = 0, tile_hi = 0;   // owned source/target tiles
+    long long tgt_base = 0;               // tile_lo * NB_TILE
+    long long n_local = 0;                // real bodies owned
+    int tpad = 0;                         // padded targets (multiple of the largest i-tile)
+    cudaStream_t compute = nullptr, comm = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_pass_done = nullptr;
+    cudaEvent_t ev_gather[2] = {nullptr, nullptr};
+    void* src[2] = {nullptr, nullptr};
+    double *acc = nullptr, *pos = nullptr, *vel = nullptr, *mass = nullptr, *forces = nullptr;
+    double* aos_dev = nullptr;            // staging image of the AoS bodies (upload/download)
+    double* energy = nullptr;             // [2]
+    unsigned *tile_done = nullptr, *sched = nullptr;
+    ncclComm_t comm_nccl = nullptr;
+    int sms = 0;
+};
+
+}  // namespace
+
+struct nb200_ctx {
+    int dim = 3;
+    size_t n = 0;
+    bool f64 = true;
+    int world = 1;                // shards over all processes
+    bool rank_mode = false;
+    bool detached = false;        // rank context without a communicator (single-GPU test hook)
+    long long ntiles = 0;         // source tiles incl. padding: world * tiles_per_shard
+    long long tiles_per_shard = 0;
+    long long nalloc = 0;         // bodies allocated in each source buffer
+    std::vector<Shard> shards;    // the shards THIS process drives
+    int cur = 0;                  // current source buffer
+    bool uploaded = false;
+    double pos_scale = 1.0, mass_scale = 1.0;
+    // options
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = 1;
+    // bookkeeping
+    long long launches = 0;
+    double last_ms = 0.0;
+    std::string error, plan;
+    size_t aos_stride = 0;
+};
+
+namespace {
+
+int fail(nb200_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->error = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(ctx, NB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+#define CKN(call)                                                                              \
+    do {                                                                                       \
+        ncclResult_t r_ = (call);                                                              \
+        if (r_ != ncclSuccess)                                                                 \
+            return fail(ctx, NB200_ENCCL, "%s failed: %s (%s:%d)", #call,                       \
+                        nccl_api()->GetErrorString(r_), __FILE__, __LINE__);                   \
+    } while (0)
+
+constexpr int kMaxItile = 1024;
+
+int alloc_shard(nb200_ctx* ctx, Shard& s) {
+    const int D = ctx->dim;
+    const size_t rs = ctx->f64 ? 8 : 4;
+    CK(cudaSetDevice(s.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, s.device));
+    if (prop.major < 10)
+        return fail(ctx, NB200_ECUDA, "device %d is sm_%d%d; libnb200 is built for sm_100a only", s.device,
+                    prop.major, prop.minor);
+    s.sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.comm, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&s.ev_start));
+    CK(cudaEventCreate(&s.ev_stop));
+    CK(cudaEventCreateWithFlags(&s.ev_pass_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_gather[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_gather[1], cudaEventDisableTiming));
+    const size_t src_bytes = (size_t)ctx->nalloc * (D + 1) * rs;
+    for (int b = 0; b < 2; ++b) CK(cudaMalloc(&s.src[b], src_bytes));
+    const size_t tp = (size_t)s.tpad;
+    CK(cudaMalloc(&s.acc, 3 * tp * sizeof(double)));
+    CK(cudaMemset(s.acc, 0, 3 * tp * sizeof(double)));
+    CK(cudaMalloc(&s.pos, (size_t)D * tp * sizeof(double)));
+    CK(cudaMalloc(&s.vel, (size_t)D * tp * sizeof(double)));
+    CK(cudaMalloc(&s.mass, tp * sizeof(double)));
+    CK(cudaMalloc(&s.forces, std::max<size_t>(1, (size_t)s.n_local * D) * sizeof(double)));
+    CK(cudaMalloc(&s.energy, 2 * sizeof(double)));
+    CK(cudaMalloc(&s.tile_done, (tp / 32 + 1) * sizeof(unsigned)));
+    CK(cudaMemset(s.tile_done, 0, (tp / 32 + 1) * sizeof(unsigned)));
+    CK(cudaMalloc(&s.sched, 2 * sizeof(unsigned)));
+    CK(cudaMemset(s.sched, 0, 2 * sizeof(unsigned)));
+    // opt in to the dynamic shared memory of every variant once
+    for (int v = 0; v < kNumVariants; ++v)
+        CK(cudaFuncSetAttribute((const void*)pick_kernel(D, ctx->f64, v),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem_bytes(D, ctx->f64)));
+    return NB200_OK;
+}
+
+void free_shard(Shard& s) {
+    cudaSetDevice(s.device);
+    if (s.compute) cudaStreamSynchronize(s.compute);
+    if (s.comm) cudaStreamSynchronize(s.comm);
+    if (s.comm_nccl && nccl_api()->CommDestroy) nccl_api()->CommDestroy(s.comm_nccl);
+    for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
+    cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
+    cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.tile_done); cudaFree(s.sched);
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
+    if (s.ev_stop) cudaEventDestroy(s.ev_stop);
+    if (s.ev_pass_done) cudaEventDestroy(s.ev_pass_done);
+    for (int b = 0; b < 2; ++b) if (s.ev_gather[b]) cudaEventDestroy(s.ev_gather[b]);
+    if (s.compute) cudaStreamDestroy(s.compute);
+    if (s.comm) cudaStreamDestroy(s.comm);
+}
+
+// geometry shared by both create paths
+int layout(nb200_ctx* ctx, int dim, size_t n, int precision, int world) {
+    if (dim != 2 && dim != 3) return fail(nullptr, NB200_EINVAL, "dim must be 2 or 3 (main.cpp:889-892), got %d", dim);
+    if (precision != NB200_FP64 && precision != NB200_FP32)
+        return fail(nullptr, NB200_EINVAL, "precision must be 64 or 32, got %d", precision);
+    if (world < 1 || world > 64) return fail(nullptr, NB200_EINVAL, "bad shard count %d", world);
+    if (n > (size_t)1 << 30) return fail(nullptr, NB200_EINVAL, "n too large");
+    ctx->dim = dim;
+    ctx->n = n;
+    ctx->f64 = precision == NB200_FP64;
+    ctx->world = world;
+    const long long tiles = std::max<long long>(1, ((long long)n + NB_TILE - 1) / NB_TILE);
+    ctx->tiles_per_shard = (tiles + world - 1) / world;
+    ctx->ntiles = ctx->tiles_per_shard * world;
+    // slack so that a padded i-tile of the last shard never reads past the buffer
+    ctx->nalloc = ctx->ntiles * NB_TILE + kMaxItile;
+    return NB200_OK;
+}
+
+void place_shard(const nb200_ctx* ctx, Shard& s, int rank, int device) {
+    s.rank = rank;
+    s.device = device;
+    s.tile_lo = rank * ctx->tiles_per_shard;
+    s.tile_hi = s.tile_lo + ctx->tiles_per_shard;
+    s.tgt_base = s.tile_lo * NB_TILE;
+    const long long hi = std::min<long long>((long long)ctx->n, s.tile_hi * NB_TILE);
+    s.n_local = std::max<long long>(0, hi - s.tgt_base);
+    const long long span = ctx->tiles_per_shard * NB_TILE;
+    s.tpad = (int)((span + kMaxItile - 1) / kMaxItile * kMaxItile);
+}
+
+// ------------------------------------------------------------------------------- launch plan
+struct Plan {
+    int variant;
+    int seg_tiles;
+    int grid;
+    int n_itiles;
+};
+
+int make_plan(nb200_ctx* ctx, const Shard& s, Plan* out) {
+    const int D = ctx->dim;
+    const long long NT = ctx->ntiles;
+    int occ = 1;
+    auto resident = [&](int v, int* grid) -> int {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &nb, (const void*)pick_kernel(D, ctx->f64, v), kVariants[v].block, smem_bytes(D, ctx->f64));
+        if (e != cudaSuccess) return -1;
+        *grid = std::max(1, nb) * s.sms;
+        return nb;
+    };
+    const long long span = ctx->tiles_per_shard * NB_TILE;   // targets incl. tile padding
+    int v = ctx->opt_variant;
+    int grid = 0;
+    if (v < 0 || v >= kNumVariants) {
+        // largest i-tile that still gives every resident CTA >= 8 units at >= 8 tiles per unit,
+        // else the smallest i-tile
+        v = kNumVariants - 1;
+        for (int c = 0; c < kNumVariants; ++c) {
+            int g = 0;
+            if (resident(c, &g) < 0) continue;
+            const long long nit = (span + kVariants[c].itile() - 1) / kVariants[c].itile();
+            const long long max_units = nit * std::max<long long>(1, NT / 8);
+            if (max_units >= 8LL * g) { v = c; break; }
+        }
+    }
+    occ = resident(v, &grid);
+    if (occ < 0) return fail(ctx, NB200_ECUDA, "occupancy query failed for variant %d", v);
+    const int itile = kVariants[v].itile();
+    const int nit = (int)((span + itile - 1) / itile);
+    int seg = ctx->opt_seg_tiles;
+    if (seg <= 0) {
+        // aim for ~64 units per resident CTA, at least 8 tiles per unit when the problem allows
+        const long long want_units = 64LL * grid;
+        long long nseg = std::max<long long>(1, (want_units + nit - 1) / nit);
+        nseg = std::min<long long>(nseg, std::max<long long>(1, NT / 8));
+        if ((long long)nit * nseg < 2LL * grid) nseg = std::min<long long>(NT, std::max<long long>(nseg, (2LL * grid + nit - 1) / nit));
+        seg = (int)((NT + nseg - 1) / nseg);
+    }
+    seg = (int)std::max<long long>(1, std::min<long long>(seg, NT));
+    if (ctx->opt_grid_mult > 0) grid = std::max(1, grid * ctx->opt_grid_mult / 16);
+    out->variant = v;
+    out->seg_tiles = seg;
+    out->grid = grid;
+    out->n_itiles = nit;
+    return NB200_OK;
+}
+
+struct Ranges {
+    int r0b, r0e, r1b, r1e;
+};
+
+int nsegs(int b, int e, int seg) { return e > b ? (e - b + seg - 1) / seg : 0; }
+
+// launch one pass of the force kernel on shard s over the given source-tile ranges
+int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsigned units_per_itile,
+                int mode, double G, double cutoff, double dt, int cur) {
+    NbForceParams P;
+    memset(&P, 0, sizeof P);
+    P.src = s.src[cur];
+    P.src_next = s.src[cur ^ 1];
+    P.acc = s.acc;
+    P.tile_done = s.tile_done;
+    P.sched = s.sched;
+    P.pos = s.pos;
+    P.vel = s.vel;
+    P.mass = s.mass;
+    P.forces = s.forces;
+    P.tgt_base = s.tgt_base;
+    P.n_local = s.n_local;
+    P.tpad = s.tpad;
+    P.n_itiles = pl.n_itiles;
+    P.seg_tiles = pl.seg_tiles;
+    P.r0_begin = rg.r0b; P.r0_end = rg.r0e; P.r1_begin = rg.r1b; P.r1_end = rg.r1e;
+    P.nseg0 = nsegs(rg.r0b, rg.r0e, pl.seg_tiles);
+    P.nseg1 = nsegs(rg.r1b, rg.r1e, pl.seg_tiles);
+    P.units_per_itile = units_per_itile;
+    P.mode = mode;
+    P.G = G;
+    // FP32 sources are scaled by powers of two: x' = x ps, m' = m ms  =>  r'^2 = r^2 ps^2,
+    // sum' = sum * ms / ps^3
+    P.cutoff = cutoff * ctx->pos_scale * ctx->pos_scale;
+    P.dt = dt;
+    P.acc_scale = (ctx->pos_scale * ctx->pos_scale * ctx->pos_scale) / ctx->mass_scale;
+    P.pos_scale = ctx->pos_scale;
+    if (P.nseg0 + P.nseg1 == 0) return NB200_OK;
+    const Variant& V = kVariants[pl.variant];
+    ForceKernel k = pick_kernel(ctx->dim, ctx->f64, pl.variant);
+    const int units = pl.n_itiles * (P.nseg0 + P.nseg1);
+    const int grid = std::min(pl.grid, units);
+    k<<<grid, V.block, smem_bytes(ctx->dim, ctx->f64), s.compute>>>(P);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return NB200_OK;
+}
+
+void describe_plan(nb200_ctx* ctx, const Plan& pl, const char* what) {
+    char buf[256];
+    const Variant& V = kVariants[pl.variant];
+    snprintf(buf, sizeof buf,
+             "%s: fp%d dim=%d n=%zu shards=%d variant=%d(TI=%d,JS=%d,block=%d,itile=%d) seg_tiles=%d "
+             "i-tiles=%d grid=%d tiles=%lld",
+             what, ctx->f64 ? 64 : 32, ctx->dim, ctx->n, ctx->world, pl.variant, V.ti, V.js, V.block, V.itile(),
+             pl.seg_tiles, pl.n_itiles, pl.grid, ctx->ntiles);
+    ctx->plan = buf;
+}
+
+int total_units_per_itile(const nb200_ctx* ctx, const Shard& s, const Plan& pl, bool split) {
+    const int NT = (int)ctx->ntiles;
+    if (!split) return nsegs(0, NT, pl.seg_tiles);
+    return nsegs((int)s.tile_lo, (int)s.tile_hi, pl.seg_tiles) + nsegs(0, (int)s.tile_lo, pl.seg_tiles) +
+           nsegs((int)s.tile_hi, NT, pl.seg_tiles);
+}
+
+int finish_timing(nb200_ctx* ctx) {
+    double worst = 0.0;
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        CK(cudaEventSynchronize(s.ev_stop));
+        CK(cudaStreamSynchronize(s.comm));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s.ev_start, s.ev_stop));
+        worst = std::max(worst, (double)ms);
+    }
+    ctx->last_ms = worst;
+    return NB200_OK;
+}
+
+int init_common(nb200_ctx* ctx) {
+    for (Shard& s : ctx->shards) {
+        int rc = alloc_shard(ctx, s);
+        if (rc) return rc;
+    }
+    return NB200_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char* nb200_version(void) { return NB200_VERSION_STR; }
+
+const char* nb200_last_error(const nb200_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+const char* nb200_plan(const nb200_ctx* ctx) { return ctx ? ctx->plan.c_str() : ""; }
+
+long long nb200_launch_count(const nb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int nb200_last_elapsed_ms(const nb200_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return NB200_EINVAL;
+    *ms = ctx->last_ms;
+    return NB200_OK;
+}
+
+int nb200_get_unique_id(void* out) {
+    if (!out) return fail(nullptr, NB200_EINVAL, "null unique id buffer");
+    NcclApi* a = nccl_api();
+    if (!a->error.empty()) return fail(nullptr, NB200_ENCCL, "%s", a->error.c_str());
+    static_assert(sizeof(ncclUniqueId) == NB200_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    ncclResult_t r = a->GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, NB200_ENCCL, "ncclGetUniqueId: %s", a->GetErrorString(r));
+    memcpy(out, &id, sizeof id);
+    return NB200_OK;
+}
+
+int nb200_create(nb200_ctx** out, int dim, size_t n, int precision, int ngpus) {
+    if (!out) return fail(nullptr, NB200_EINVAL, "null out pointer");
+    *out = nullptr;
+    int have = 0;
+    cudaError_t e = cudaGetDeviceCount(&have);
+    if (e != cudaSuccess || have == 0)
+        return fail(nullptr, NB200_ECUDA, "no CUDA device: %s (libnb200 has no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (ngpus < 1 || ngpus > have) return fail(nullptr, NB200_EINVAL, "ngpus=%d but %d device(s) visible", ngpus, have);
+    nb200_ctx* ctx = new nb200_ctx();
+    int rc = layout(ctx, dim, n, precision, ngpus);
+    if (rc) { delete ctx; return rc; }
+    std::vector<int> devs;
+    if (const char* env = getenv("NB200_DEVICES")) {
+        for (const char* p = env; *p && (int)devs.size() < ngpus;) {
+            devs.push_back(atoi(p));
+            p = strchr(p, ',');
+            if (!p) break;
+            ++p;
+        }
+    }
+    for (int i = (int)devs.size(); i < ngpus; ++i) devs.push_back(i);
+    ctx->shards.resize(ngpus);
+    for (int g = 0; g < ngpus; ++g) place_shard(ctx, ctx->shards[g], g, devs[g]);
+    rc = init_common(ctx);
+    if (rc == NB200_OK && ngpus > 1) {
+        NcclApi* a = nccl_api();
+        if (!a->error.empty()) rc = fail(ctx, NB200_ENCCL, "%s", a->error.c_str());
+        else {
+            std::vector<ncclComm_t> comms(ngpus);
+            ncclResult_t r = a->CommInitAll(comms.data(), ngpus, devs.data());
+            if (r != ncclSuccess) rc = fail(ctx, NB200_ENCCL, "ncclCommInitAll: %s", a->GetErrorString(r));
+            else for (int g = 0; g < ngpus; ++g) ctx->shards[g].comm_nccl = comms[g];
+        }
+    }
+    if (rc) {
+        g_create_error = ctx->error;
+        nb200_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return NB200_OK;
+}
+
+int nb200_create_rank(nb200_ctx** out, int dim, size_t n, int precision, int device, int rank, int world,
+                      const void* unique_id) {
+    if (!out) return fail(nullptr, NB200_EINVAL, "null out pointer");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return fail(nullptr, NB200_EINVAL, "bad rank %d / world %d", rank, world);
+    // unique_id == NULL with world > 1 builds a DETACHED shard (no communicator): forces() works,
+    // step() is limited to nsteps == 1 (the other shards' rows of the next buffer are not refreshed;
+    // re-upload before stepping again).  This is the "virtual rank" hook SURVEY.md section 4 asks for so
+    // that the sharded passes can be exercised on one GPU.
+    int have = 0;
+    cudaError_t e = cudaGetDeviceCount(&have);
+    if (e != cudaSuccess || have == 0)
+        return fail(nullptr, NB200_ECUDA, "no CUDA device: %s (libnb200 has no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= have) return fail(nullptr, NB200_EINVAL, "device %d not visible (%d devices)", device, have);
+    nb200_ctx* ctx = new nb200_ctx();
+    int rc = layout(ctx, dim, n, precision, world);
+    if (rc) { delete ctx; return rc; }
+    ctx->rank_mode = true;
+    ctx->shards.resize(1);
+    place_shard(ctx, ctx->shards[0], rank, device);
+    rc = init_common(ctx);
+    ctx->detached = world > 1 && !unique_id;
+    if (rc == NB200_OK && world > 1 && unique_id) {
+        NcclApi* a = nccl_api();
+        if (!a->error.empty()) rc = fail(ctx, NB200_ENCCL, "%s", a->error.c_str());
+        else {
+            ncclUniqueId id;
+            memcpy(&id, unique_id, sizeof id);
+            cudaSetDevice(device);
+            ncclResult_t r = a->CommInitRank(&ctx->shards[0].comm_nccl, world, id, rank);
+            if (r != ncclSuccess) rc = fail(ctx, NB200_ENCCL, "ncclCommInitRank: %s", a->GetErrorString(r));
+        }
+    }
+    if (rc) {
+        g_create_error = ctx->error;
+        nb200_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return NB200_OK;
+}
+
+void nb200_destroy(nb200_ctx* ctx) {
+    if (!ctx) return;
+    for (Shard& s : ctx->shards) free_shard(s);
+    delete ctx;
+}
+
+int nb200_shard_range(const nb200_ctx* ctx, size_t* lo, size_t* hi) {
+    if (!ctx || !lo || !hi) return NB200_EINVAL;
+    if (!ctx->rank_mode) { *lo = 0; *hi = ctx->n; return NB200_OK; }
+    const Shard& s = ctx->shards[0];
+    *lo = (size_t)std::min<long long>(s.tgt_base, (long long)ctx->n);
+    *hi = *lo + (size_t)s.n_local;
+    return NB200_OK;
+}
+
+int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
+    if (!ctx || !key) return NB200_EINVAL;
+    if (!strcmp(key, "variant")) ctx->opt_variant = (value >= 0 && value < kNumVariants) ? (int)value : -1;
+    else if (!strcmp(key, "seg_tiles")) ctx->opt_seg_tiles = (int)std::max(0L, value);
+    else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);
+    else if (!strcmp(key, "overlap")) ctx->opt_overlap = value != 0;
+    else return fail(ctx, NB200_EINVAL, "unknown option '%s'", key);
+    return NB200_OK;
+}
+
+int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
+    if (!ctx) return NB200_EINVAL;
+    const int D = ctx->dim;
+    const size_t min_stride = (size_t)(2 * D + 1) * sizeof(double);
+    if (ctx->n && !bodies) return fail(ctx, NB200_EINVAL, "null bodies");
+    if (stride < min_stride || stride % sizeof(double))
+        return fail(ctx, NB200_EINVAL, "stride %zu: Body<%d> needs >= %zu bytes, multiple of 8", stride, D, min_stride);
+    ctx->aos_stride = stride;
+    const size_t sd = stride / sizeof(double);
+    // FP32 pair math runs on power-of-two-scaled sources (exact): |x'| <= 1, m' <= 1
+    ctx->pos_scale = ctx->mass_scale = 1.0;
+    if (!ctx->f64 && ctx->n) {
+        double xmax = 0.0, mmax = 0.0;
+        const double* p = static_cast<const double*>(bodies);
+        for (size_t i = 0; i < ctx->n; ++i) {
+            const double* r = p + i * sd;
+            for (int d = 0; d < D; ++d) xmax = std::max(xmax, fabs(r[d]));
+            mmax = std::max(mmax, fabs(r[2 * D]));
+        }
+        int ex = 0;
+        if (xmax > 0 && isfinite(xmax)) { frexp(xmax, &ex); ctx->pos_scale = ldexp(1.0, -ex); }
+        if (mmax > 0 && isfinite(mmax)) { frexp(mmax, &ex); ctx->mass_scale = ldexp(1.0, -ex); }
+    }
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        const size_t bytes = std::max<size_t>(1, ctx->n) * stride;
+        if (!s.aos_dev) CK(cudaMalloc(&s.aos_dev, bytes));
+        if (ctx->n) CK(cudaMemcpyAsync(s.aos_dev, bodies, ctx->n * stride, cudaMemcpyHostToDevice, s.compute));
+        const int threads = 256;
+        const int blocks = (int)((ctx->nalloc + threads - 1) / threads);
+#define NB_PACK(DD, RR)                                                                              \
+    nb_pack_kernel<DD, RR><<<blocks, threads, 0, s.compute>>>(                                       \
+        s.aos_dev, sd, (long long)ctx->n, ctx->nalloc, (RR*)s.src[0], (RR*)s.src[1], ctx->pos_scale, \
+        ctx->mass_scale, s.tgt_base, s.tpad, s.pos, s.vel, s.mass)
+        if (D == 3) { if (ctx->f64) NB_PACK(3, double); else NB_PACK(3, float); }
+        else        { if (ctx->f64) NB_PACK(2, double); else NB_PACK(2, float); }
+#undef NB_PACK
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        CK(cudaStreamSynchronize(s.compute));
+    }
+    ctx->cur = 0;
+    ctx->uploaded = true;
+    return NB200_OK;
+}
+
+int nb200_download_aos(nb200_ctx* ctx, void* bodies, size_t stride) {
+    if (!ctx) return NB200_EINVAL;
+    if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "download before upload");
+    const int D = ctx->dim;
+    if (stride < (size_t)(2 * D + 1) * sizeof(double) || stride % sizeof(double))
+        return fail(ctx, NB200_EINVAL, "bad stride %zu", stride);
+    if (ctx->n && !bodies) return fail(ctx, NB200_EINVAL, "null bodies");
+    const size_t sd = stride / sizeof(double);
+    for (Shard& s : ctx->shards) {
+        if (s.n_local <= 0) continue;
+        CK(cudaSetDevice(s.device));
+        // reuse the staging image: rows [tgt_base, tgt_base+n_local) hold pos/vel, mass as uploaded
+        if (stride != ctx->aos_stride) return fail(ctx, NB200_EINVAL, "download stride %zu != upload stride %zu", stride, ctx->aos_stride);
+        double* rows = s.aos_dev + (size_t)s.tgt_base * sd;
+        const int threads = 256;
+        const int blocks = (int)((s.n_local + threads - 1) / threads);
+        if (D == 3) nb_unpack_kernel<3><<<blocks, threads, 0, s.compute>>>(rows, sd, s.n_local, s.tpad, s.pos, s.vel);
+        else nb_unpack_kernel<2><<<blocks, threads, 0, s.compute>>>(rows, sd, s.n_local, s.tpad, s.pos, s.vel);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        // copy only position+velocity of each row so the caller's masses stay untouched
+        CK(cudaMemcpy2DAsync(static_cast<char*>(bodies) + (size_t)s.tgt_base * stride, stride, rows, stride,
+                             (size_t)2 * D * sizeof(double), (size_t)s.n_local, cudaMemcpyDeviceToHost, s.compute));
+    }
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        CK(cudaStreamSynchronize(s.compute));
+    }
+    return NB200_OK;
+}
+
+int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out) {
+    if (!ctx) return NB200_EINVAL;
+    if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "forces before upload");
+    if (ctx->n && !forces_out) return fail(ctx, NB200_EINVAL, "null forces_out");
+    const int D = ctx->dim;
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        Plan pl;
+        int rc = make_plan(ctx, s, &pl);
+        if (rc) return rc;
+        if (&s == &ctx->shards[0]) describe_plan(ctx, pl, "forces");
+        CK(cudaStreamWaitEvent(s.compute, s.ev_gather[ctx->cur], 0));
+        CK(cudaEventRecord(s.ev_start, s.compute));
+        Ranges all = {0, (int)ctx->ntiles, 0, 0};
+        rc = launch_pass(ctx, s, pl, all, (unsigned)total_units_per_itile(ctx, s, pl, false), 0, G, cutoff_r2, 0.0, ctx->cur);
+        if (rc) return rc;
+        CK(cudaEventRecord(s.ev_stop, s.compute));
+        if (s.n_local > 0)
+            CK(cudaMemcpyAsync(forces_out + (size_t)s.tgt_base * D, s.forces, (size_t)s.n_local * D * sizeof(double),
+                               cudaMemcpyDeviceToHost, s.compute));
+    }
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        CK(cudaStreamSynchronize(s.compute));
+    }
+    return finish_timing(ctx);
+}
+
+int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps) {
+    if (!ctx) return NB200_EINVAL;
+    if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "step before upload");
+    if (nsteps < 0) return fail(ctx, NB200_EINVAL, "nsteps < 0");
+    if (ctx->detached && nsteps > 1)
+        return fail(ctx, NB200_ESTATE, "detached shard (no communicator): only nsteps == 1 is defined");
+    const bool split = ctx->world > 1 && ctx->opt_overlap;
+    const bool multi = ctx->world > 1 && !ctx->detached;
+    NcclApi* nccl = multi ? nccl_api() : nullptr;
+    std::vector<Plan> plans(ctx->shards.size());
+    for (size_t i = 0; i < ctx->shards.size(); ++i) {
+        CK(cudaSetDevice(ctx->shards[i].device));
+        int rc = make_plan(ctx, ctx->shards[i], &plans[i]);
+        if (rc) return rc;
+    }
+    describe_plan(ctx, plans[0], split ? "step(local|gather|remote)" : "step");
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        CK(cudaEventRecord(s.ev_start, s.compute));
+    }
+    const int NT = (int)ctx->ntiles;
+    const size_t rs = ctx->f64 ? 8 : 4;
+    const size_t shard_elems = (size_t)ctx->tiles_per_shard * NB_TILE * (ctx->dim + 1);
+    for (int step = 0; step < nsteps; ++step) {
+        const int cur = ctx->cur, nxt = cur ^ 1;
+        for (size_t i = 0; i < ctx->shards.size(); ++i) {
+            Shard& s = ctx->shards[i];
+            const Plan& pl = plans[i];
+            CK(cudaSetDevice(s.device));
+            const unsigned upi = (unsigned)total_units_per_itile(ctx, s, pl, split);
+            int rc;
+            if (split) {
+                Ranges own = {(int)s.tile_lo, (int)s.tile_hi, 0, 0};
+                rc = launch_pass(ctx, s, pl, own, upi, 1, G, cutoff_r2, dt, cur);
+                if (rc) return rc;
+                CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
+                Ranges rest = {0, (int)s.tile_lo, (int)s.tile_hi, NT};
+                rc = launch_pass(ctx, s, pl, rest, upi, 1, G, cutoff_r2, dt, cur);
+            } else {
+                CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
+                Ranges all = {0, NT, 0, 0};
+                rc = launch_pass(ctx, s, pl, all, upi, 1, G, cutoff_r2, dt, cur);
+            }
+            if (rc) return rc;
+            if (multi) {
+                CK(cudaEventRecord(s.ev_pass_done, s.compute));
+                CK(cudaStreamWaitEvent(s.comm, s.ev_pass_done, 0));
+            }
+        }
+        if (multi) {
+            // in-place all-gather of the freshly integrated shards into the next source buffer
+            if (ctx->shards.size() > 1) CKN(nccl->GroupStart());
+            for (Shard& s : ctx->shards) {
+                CK(cudaSetDevice(s.device));
+                char* base = static_cast<char*>(s.src[nxt]);
+                CKN(nccl->AllGather(base + (size_t)s.rank * shard_elems * rs, base, shard_elems,
+                                    ctx->f64 ? ncclDouble : ncclFloat, s.comm_nccl, s.comm));
+            }
+            if (ctx->shards.size() > 1) CKN(nccl->GroupEnd());
+            for (Shard& s : ctx->shards) {
+                CK(cudaSetDevice(s.device));
+                CK(cudaEventRecord(s.ev_gather[nxt], s.comm));
+            }
+        }
+        ctx->cur = nxt;
+    }
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        if (multi) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[ctx->cur], 0));
+        CK(cudaEventRecord(s.ev_stop, s.compute));
+    }
+    return finish_timing(ctx);
+}
+
+int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, double* potential) {
+    if (!ctx || !kinetic || !potential) return NB200_EINVAL;
+    if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "energy before upload");
+    double ke = 0.0, pe = 0.0;
+    const double cs = cutoff_r2 * ctx->pos_scale * ctx->pos_scale;
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        CK(cudaStreamWaitEvent(s.compute, s.ev_gather[ctx->cur], 0));
+        CK(cudaMemsetAsync(s.energy, 0, 2 * sizeof(double), s.compute));
+        if (s.n_local > 0) {
+            const int threads = 256;
+            const int blocks = (int)((s.n_local + threads - 1) / threads);
+#define NB_EN(DD, RR)                                                                                   \
+    nb_energy_kernel<DD, RR><<<blocks, threads, 0, s.compute>>>(                                         \
+        (const RR*)s.src[ctx->cur], ctx->ntiles, s.tgt_base, s.n_local, s.tpad, s.vel, s.mass, G, cs,    \
+        1.0 / ctx->pos_scale, 1.0 / ctx->mass_scale, s.energy)
+            if (ctx->dim == 3) { if (ctx->f64) NB_EN(3, double); else NB_EN(3, float); }
+            else               { if (ctx->f64) NB_EN(2, double); else NB_EN(2, float); }
+#undef NB_EN
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
+    }
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        double h[2];
+        CK(cudaMemcpyAsync(h, s.energy, sizeof h, cudaMemcpyDeviceToHost, s.compute));
+        CK(cudaStreamSynchronize(s.compute));
+        ke += h[0];
+        pe += h[1];
+    }
+    *kinetic = ke;
+    *potential = pe;
+    return NB200_OK;
+}
+
+int nb200_accuracy_pct(nb200_ctx* ctx, const double* forces, const double* reference, double* pct) {
+    if (!ctx || !pct || (ctx->n && (!forces || !reference))) return NB200_EINVAL;
+    const int D = ctx->dim;
+    size_t ok = 0;
+    for (size_t i = 0; i < ctx->n; ++i) {
+        bool good = true;
+        for (int d = 0; d < D && good; ++d) {
+            const double r = reference[i * D + d], f = forces[i * D + d];
+            if (fabs(r) < 1e-20) good = !(fabs(f) > 1e-9);
+            else good = !(fabs((f - r) / r) > 0.01);
+        }
+        ok += good;
+    }
+    *pct = ctx->n ? 100.0 * (double)ok / (double)ctx->n : 0.0;
+    return NB200_OK;
+}
+
+}  // extern "C"

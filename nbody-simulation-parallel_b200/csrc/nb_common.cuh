@@ -1,0 +1,96 @@
+// nb_common.cuh -- shared definitions for the B200 brute-force N-body kernels.
+//
+// Data layout in HBM ("tile-planar" SoA): bodies are grouped in tiles of NB_TILE; inside a
+// tile the D coordinates and the mass are separate contiguous planes:
+//     [tile t] = x[NB_TILE] | y[NB_TILE] | (z[NB_TILE]) | m[NB_TILE]        (NP = D+1 planes)
+// so that (a) one tile is ONE contiguous block (a single cp.async.bulk / TMA copy, and a
+// rank's shard is one contiguous all-gather chunk), and (b) LDS.128 of a plane yields four
+// consecutive sources = two packed f32x2 operands with no shuffling.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define NB_TILE 256          // sources per tile (one TMA bulk copy)
+#define NB_STAGES 3          // TMA ring depth
+
+struct NbForceParams {
+    const void* src;         // current tile-planar sources, all npad bodies (float or double)
+    void* src_next;          // next-step tile-planar sources (step mode; own shard rows written)
+    double* acc;             // [3][tpad] FP64 partial-sum accumulators of the own targets
+    unsigned* tile_done;     // [n_itiles] units finished per i-tile (self-resetting)
+    unsigned* sched;         // [2] dynamic unit counter + exit counter (self-resetting)
+    double* pos;             // [D][tpad] master positions of own targets (FP64)
+    double* vel;             // [D][tpad] master velocities
+    const double* mass;      // [tpad]    master masses
+    double* forces;          // [n_local][D] AoS Vector<D> output (forces mode)
+    long long tgt_base;      // global body index of own target 0 (multiple of NB_TILE)
+    long long n_local;       // real (unpadded) own targets
+    int tpad;                // padded own targets (multiple of the i-tile)
+    int n_itiles;            // tpad / ITILE
+    int seg_tiles;           // source tiles per unit
+    int r0_begin, r0_end;    // first source-tile range of this launch
+    int r1_begin, r1_end;    // second source-tile range (may be empty)
+    int nseg0, nseg1;        // segments per range
+    unsigned units_per_itile;  // units that must finish (over ALL launches of the step) per i-tile
+    int mode;                // 0 = forces, 1 = step (integrate in the epilogue)
+    double G;                // gravitational constant (utils.h:21 in the reference)
+    double cutoff;           // r^2 cut-off in SOURCE units (scaled for the FP32 path)
+    double dt;
+    double acc_scale;        // S = acc * acc_scale      (undo the FP32 power-of-two scaling)
+    double pos_scale;        // source = pos * pos_scale (FP32 path; 1.0 for FP64)
+};
+
+// ------------------------------------------------------------------ mbarrier / TMA (sm_90+ PTX)
+__device__ __forceinline__ uint32_t nb_smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void nb_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nb_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void nb_fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void nb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nb_smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void nb_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nb_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void nb_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NB_DONE_%=;\n"
+        "bra NB_WAIT_%=;\n"
+        "NB_DONE_%=:\n"
+        "}\n" ::"r"(nb_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void nb_tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                               uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(nb_smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(nb_smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ float nb_rcp_f32(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // bare MUFU.RCP
+    return y;
+}
+// 1/x for a normal positive double: MUFU.RCP64H seed (~2^-20) + one cubic step -> < 1.5 ulp.
+__device__ __forceinline__ double nb_rcp_f64(double x) {
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    double e = fma(-x, y0, 1.0);
+    double p = fma(e, e, e);
+    return fma(y0, p, y0);
+}

@@ -1,0 +1,93 @@
+"""Seeded synthetic body sets (harness inputs; numpy only, no GPU, no oracle).
+
+The reference's only generator is unseeded (``generate_random_bodies<D>``, utils.h:107-135:
+``std::random_device``), so identical bytes cannot be fed to two implementations with it.  These
+generators reproduce its RANGES where the config asks for them and add the two distributions
+BASELINE.json names (uniform cube, Plummer sphere).  Output layout is the reference's AoS
+``Body<D>`` (body.h:7-19): float64 array (n, 2*D+1) = position[D], velocity[D], mass.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+#: utils.h:21
+G_REF = 4.471e-21
+
+
+def reference_range(n: int, dim: int = 3, seed: int = 42) -> np.ndarray:
+    """The reference generator's ranges (utils.h:113-115), seeded: pos U[1,1e7], vel U[-10,10],
+    mass U[1,1e8]."""
+    rng = np.random.default_rng(seed)
+    b = np.empty((n, 2 * dim + 1))
+    b[:, :dim] = rng.uniform(1.0, 1.0e7, (n, dim))
+    b[:, dim:2 * dim] = rng.uniform(-10.0, 10.0, (n, dim))
+    b[:, 2 * dim] = rng.uniform(1.0, 1.0e8, n)
+    return b
+
+
+def uniform_cube(n: int, dim: int = 3, seed: int = 42, G: float = G_REF) -> np.ndarray:
+    """Unit cube/square: pos U[0,1)^D, vel U[-0.1,0.1], mass U[0.5,1.5]/(G n) so that
+    G * sum(m) ~ 1 and the dynamics are non-trivial with the reference's tiny G."""
+    rng = np.random.default_rng(seed)
+    b = np.empty((n, 2 * dim + 1))
+    b[:, :dim] = rng.random((n, dim))
+    b[:, dim:2 * dim] = rng.uniform(-0.1, 0.1, (n, dim))
+    b[:, 2 * dim] = rng.uniform(0.5, 1.5, n) / (G * max(n, 1))
+    return b
+
+
+def plummer(n: int, seed: int = 42, G: float = G_REF, a: float = 1.0, rmax: float = 22.8) -> np.ndarray:
+    """3D Plummer sphere (scale a), equal masses 1/(G n): r = a (u^(-2/3) - 1)^(-1/2) truncated
+    at rmax*a, isotropic directions; speeds by the standard q^2 (1-q^2)^(7/2) rejection times the
+    local escape speed sqrt(2) (1 + r^2)^(-1/4)."""
+    rng = np.random.default_rng(seed)
+    r = np.empty(n)
+    filled = 0
+    while filled < n:
+        u = rng.random(n - filled)
+        u = u[u > 0]
+        rr = a / np.sqrt(u ** (-2.0 / 3.0) - 1.0)
+        rr = rr[rr < rmax * a]
+        r[filled:filled + rr.size] = rr
+        filled += rr.size
+
+    def iso(k):
+        z = rng.uniform(-1.0, 1.0, k)
+        phi = rng.uniform(0.0, 2.0 * np.pi, k)
+        s = np.sqrt(1.0 - z * z)
+        return np.stack([s * np.cos(phi), s * np.sin(phi), z], axis=1)
+
+    q = np.empty(n)
+    filled = 0
+    while filled < n:
+        k = n - filled
+        x = rng.random(2 * k)
+        y = rng.random(2 * k) * 0.1
+        ok = x[y < x * x * (1.0 - x * x) ** 3.5][:k]
+        q[filled:filled + ok.size] = ok
+        filled += ok.size
+    speed = q * np.sqrt(2.0) * (1.0 + (r / a) ** 2) ** (-0.25)
+    b = np.empty((n, 7))
+    b[:, 0:3] = iso(n) * r[:, None]
+    b[:, 3:6] = iso(n) * speed[:, None]
+    b[:, 6] = 1.0 / (G * max(n, 1))
+    return b
+
+
+def round_to_float(bodies: np.ndarray) -> np.ndarray:
+    """Positions and masses rounded to float32 and widened back: what the FP32 pair kernel sees.
+    The <=1e-5 FP32 criterion compares against the FP64 oracle fed THESE inputs."""
+    dim = (bodies.shape[1] - 1) // 2
+    b = np.array(bodies, dtype=np.float64, copy=True)
+    b[:, :dim] = b[:, :dim].astype(np.float32).astype(np.float64)
+    b[:, 2 * dim] = b[:, 2 * dim].astype(np.float32).astype(np.float64)
+    return b
+
+
+def relative_norm_error(f: np.ndarray, ref: np.ndarray) -> np.ndarray:
+    """Per-body norm-wise relative error ||f_i - ref_i||_2 / ||ref_i||_2 (SURVEY section 4 lesson i).
+    Bodies whose reference force is exactly zero compare absolutely (error 0 iff f_i == 0)."""
+    num = np.linalg.norm(np.asarray(f) - np.asarray(ref), axis=1)
+    den = np.linalg.norm(np.asarray(ref), axis=1)
+    out = np.where(den > 0, num / np.where(den > 0, den, 1.0), np.where(num > 0, np.inf, 0.0))
+    return out
