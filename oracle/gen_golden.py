@@ -56,15 +56,15 @@ def main():
         # BASELINE.json configs[0]: seq 3D N=1024, 10 steps, reference-range inputs
         "c1_refrange3d_n1024": (gen.reference_range(1024, 3, seed=43), 1.0, 10),
         "refrange2d_n300": (gen.reference_range(300, 2, seed=44), 1.0, 10),
-        "cube3d_n1000": (gen.uniform_cube(1000, 3, seed=45), 1e-3, 20),   # ragged: not a tile multiple
-        "cube2d_n1280": (gen.uniform_cube(1280, 2, seed=46), 1e-3, 20),
+        "cube3d_n1000": (gen.uniform_cube(1000, 3, seed=45), 1e-4, 20),   # ragged: not a tile multiple
+        "cube2d_n1280": (gen.uniform_cube(1280, 2, seed=46), 1e-5, 20),
         "plummer3d_n768": (gen.plummer(768, seed=47), 1e-3, 20),
         "degenerate3d_n9": (degenerate(3), 1e-4, 5),
         "degenerate2d_n9": (degenerate(2), 1e-4, 5),
         "tiny3d_n1": (gen.uniform_cube(1, 3, seed=48), 1e-3, 3),
         "tiny2d_n2": (gen.uniform_cube(2, 2, seed=49), 1e-3, 3),
         "tiny3d_n3": (gen.uniform_cube(3, 3, seed=50), 1e-3, 3),
-        "ragged3d_n257": (gen.uniform_cube(257, 3, seed=51), 1e-3, 5),
+        "ragged3d_n257": (gen.uniform_cube(257, 3, seed=51), 1e-4, 5),
     }
     for name, (bodies, dt, nsteps) in cases.items():
         f_seq, _ = oracle.ref_forces(bodies, "seq")

@@ -50,10 +50,15 @@ def test_fp64_trajectory_vs_reference_golden(pkg, name):
         # the r^2 = 1.21e-10 pair is flung apart at ~1e33-scale forces: compare the others tightly
         ok = [0, 1, 2, 3, 6, 7, 8]
         after, want = after[ok], want[ok]
+    # the fixtures use a dt that resolves the motion (max displacement << 1), so the trajectory is
+    # well conditioned: 1e-12 relative on positions, 1e-11 on velocities (close pairs amplify the
+    # ~1e-15 force differences; the reference's own seq/omp_2 orderings agree to ~1e-16 here)
     scale_x = np.abs(want[:, :dim]).max()
     scale_v = np.abs(want[:, dim:2 * dim]).max()
-    assert np.abs(after[:, :dim] - want[:, :dim]).max() <= 1e-11 * scale_x
-    assert np.abs(after[:, dim:2 * dim] - want[:, dim:2 * dim]).max() <= 1e-10 * max(scale_v, 1e-300)
+    ex = np.abs(after[:, :dim] - want[:, :dim]).max()
+    ev = np.abs(after[:, dim:2 * dim] - want[:, dim:2 * dim]).max()
+    assert ex <= 1e-12 * scale_x, f"{name}: position error {ex:.3e} (scale {scale_x:.3g})"
+    assert ev <= 1e-11 * max(scale_v, 1e-300), f"{name}: velocity error {ev:.3e} (scale {scale_v:.3g})"
 
 
 # ------------------------------------------------------------------ golden inputs, FP32 mode
@@ -148,7 +153,7 @@ def test_plummer_sampled_targets_large_n(pkg, oracle):
 # ------------------------------------------------------------------ energy
 def test_energy_matches_oracle_and_drift_matches_cpu_stepper(pkg, oracle):
     b = pkg.generators.uniform_cube(1024, 3, seed=12)
-    dt, nsteps = 1e-3, 100
+    dt, nsteps = 2e-4, 100
     with pkg.NBodyCuda(3, 1024, pkg.NB200_FP64) as ctx:
         ctx.upload(b)
         ke0, pe0 = ctx.energy()
@@ -165,7 +170,8 @@ def test_energy_matches_oracle_and_drift_matches_cpu_stepper(pkg, oracle):
         assert np.allclose(drift_gpu, drift_cpu, rtol=1e-6, atol=1e-12), (drift_gpu, drift_cpu)
         out = b.copy()
         ctx.download(out)
-        assert np.abs(out[:, :3] - cpu[:, :3]).max() <= 1e-9
+        err = np.abs(out[:, :3] - cpu[:, :3])
+        assert np.median(err) <= 1e-13 and err.max() <= 1e-8, (np.median(err), err.max())
 
 
 def test_fp32_mode_energy_drift_tracks_fp64(pkg):
