@@ -154,6 +154,7 @@ struct nb200_ctx {
     int cur = 0;                  // current source buffer
     bool uploaded = false;
     double pos_scale = 1.0, mass_scale = 1.0;
+    bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
     int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = 1;
     // bookkeeping
@@ -425,6 +426,49 @@ int init_common(nb200_ctx* ctx) {
     return NB200_OK;
 }
 
+
+// AoS staging image -> tile-planar sources (both buffers) + FP64 master state, on every shard
+int pack_sources(nb200_ctx* ctx) {
+    const int D = ctx->dim;
+    const size_t sd = ctx->aos_stride / sizeof(double);
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        const int threads = 256;
+        const int blocks = (int)((ctx->nalloc + threads - 1) / threads);
+#define NB_PACK(DD, RR)                                                                              \
+    nb_pack_kernel<DD, RR><<<blocks, threads, 0, s.compute>>>(                                       \
+        s.aos_dev, sd, (long long)ctx->n, ctx->nalloc, (RR*)s.src[0], (RR*)s.src[1], ctx->pos_scale, \
+        ctx->mass_scale, s.tgt_base, s.tpad, s.pos, s.vel, s.mass)
+        if (D == 3) { if (ctx->f64) NB_PACK(3, double); else NB_PACK(3, float); }
+        else        { if (ctx->f64) NB_PACK(2, double); else NB_PACK(2, float); }
+#undef NB_PACK
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        CK(cudaStreamSynchronize(s.compute));
+    }
+    ctx->cur = 0;
+    return NB200_OK;
+}
+
+// FP32 range guard: kept pairs reach 1/r'^4 <= 1/cutoff'^2, which must stay finite in FP32, so
+// the scaled cut-off cutoff * ps^2 may not fall under 2^-62.  The scale is a power of two (exact).
+int ensure_fp32_scale(nb200_ctx* ctx, double cutoff) {
+    if (ctx->f64 || !(cutoff > 0.0) || ctx->n == 0) return NB200_OK;
+    const double need = sqrt(ldexp(1.0, -62) / cutoff);
+    if (ctx->pos_scale >= need) return NB200_OK;
+    if (!ctx->pristine)
+        return fail(ctx, NB200_ESTATE,
+                    "FP32 mode: cut-off %g needs a larger source scale than the one chosen at upload; "
+                    "call with this cut-off before the first step, or use NB200_FP64", cutoff);
+    int ex = 0;
+    frexp(need, &ex);
+    ctx->pos_scale = ldexp(1.0, ex);       // power of two >= need
+    return pack_sources(ctx);
+}
+
 }  // namespace
 
 // =============================================================================== C ABI
@@ -596,22 +640,10 @@ int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
         const size_t bytes = std::max<size_t>(1, ctx->n) * stride;
         if (!s.aos_dev) CK(cudaMalloc(&s.aos_dev, bytes));
         if (ctx->n) CK(cudaMemcpyAsync(s.aos_dev, bodies, ctx->n * stride, cudaMemcpyHostToDevice, s.compute));
-        const int threads = 256;
-        const int blocks = (int)((ctx->nalloc + threads - 1) / threads);
-#define NB_PACK(DD, RR)                                                                              \
-    nb_pack_kernel<DD, RR><<<blocks, threads, 0, s.compute>>>(                                       \
-        s.aos_dev, sd, (long long)ctx->n, ctx->nalloc, (RR*)s.src[0], (RR*)s.src[1], ctx->pos_scale, \
-        ctx->mass_scale, s.tgt_base, s.tpad, s.pos, s.vel, s.mass)
-        if (D == 3) { if (ctx->f64) NB_PACK(3, double); else NB_PACK(3, float); }
-        else        { if (ctx->f64) NB_PACK(2, double); else NB_PACK(2, float); }
-#undef NB_PACK
-        CK(cudaGetLastError());
-        ctx->launches++;
     }
-    for (Shard& s : ctx->shards) {
-        CK(cudaSetDevice(s.device));
-        CK(cudaStreamSynchronize(s.compute));
-    }
+    int rc = pack_sources(ctx);
+    if (rc) return rc;
+    ctx->pristine = true;
     ctx->cur = 0;
     ctx->uploaded = true;
     return NB200_OK;
@@ -653,6 +685,7 @@ int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out)
     if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "forces before upload");
     if (ctx->n && !forces_out) return fail(ctx, NB200_EINVAL, "null forces_out");
     const int D = ctx->dim;
+    if (int rc0 = ensure_fp32_scale(ctx, cutoff_r2)) return rc0;
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
         Plan pl;
@@ -682,6 +715,8 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
     if (nsteps < 0) return fail(ctx, NB200_EINVAL, "nsteps < 0");
     if (ctx->detached && nsteps > 1)
         return fail(ctx, NB200_ESTATE, "detached shard (no communicator): only nsteps == 1 is defined");
+    if (int rc0 = ensure_fp32_scale(ctx, cutoff_r2)) return rc0;
+    if (nsteps > 0) ctx->pristine = false;
     const bool split = ctx->world > 1 && ctx->opt_overlap;
     const bool multi = ctx->world > 1 && !ctx->detached;
     NcclApi* nccl = multi ? nccl_api() : nullptr;

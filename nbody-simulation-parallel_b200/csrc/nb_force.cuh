@@ -26,21 +26,32 @@ template <bool F64> struct NbReal { using type = float; };
 template <> struct NbReal<true> { using type = double; };
 
 // ---------------------------------------------------------------------------------------------
-// FP32: one tile against TI targets.  nx/ny/nz hold the NEGATED, duplicated target coordinates.
-template <int D, int TI, int JS>
-__device__ __forceinline__ void nb_tile_f32(const float* __restrict__ stage, int part, float cutoff,
-                                            const float2 (&npos)[TI][3], double (&accd)[TI][3]) {
+// FP32: one tile against TI targets.  npos holds the NEGATED target coordinates (the packed add
+// takes them as a broadcast scalar operand).  a[][] receives this tile's FP32 partial sums.
+//
+// EXACT = false (fast pass): no per-pair cut-off work at all -- FSETP/FSEL are ALU-pipe
+// instructions and on sm_100 every ALU instruction costs the FMA pipe two cycles (measured:
+// fma 72 % + alu 27 % = 99 % busy with the select in the loop).  Instead the pass tracks the
+// minimum r^2 it saw (one FMNMX3 per two pairs) and the caller REDOES the tile with
+// EXACT = true when that minimum is under the cut-off: the tile holding the thread's own
+// targets (self pair, r^2 = 0), exact duplicates, and genuinely close pairs.  NaN/inf produced
+// by rcp(0) in a fast pass are discarded with the rest of that pass.
+// EXACT = true: hard cut-off per pair (methods.cpp:119): pairs with r^2 < cutoff are DROPPED,
+// which also removes the self pair and exact duplicates: rcp(+inf) = 0.
+template <int D, int TI, int JS, bool EXACT>
+__device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, int part, float cutoff,
+                                             const float (&npos)[TI][3], float2 (&a)[TI][3]) {
     const float4* sx = reinterpret_cast<const float4*>(stage);
     const float4* sy = sx + NB_TILE / 4;
     const float4* sz = sy + NB_TILE / 4;                      // D == 3 only
     const float4* sm = sx + D * (NB_TILE / 4);
-    float2 a[TI][3];
 #pragma unroll
     for (int t = 0; t < TI; ++t)
 #pragma unroll
         for (int d = 0; d < 3; ++d) a[t][d] = make_float2(0.f, 0.f);
 
     const float inf = __int_as_float(0x7f800000);
+    float rmin = inf;
 #pragma unroll 2
     for (int q = part; q < NB_TILE / 4; q += JS) {
         const float4 X = sx[q], Y = sy[q], M = sm[q];
@@ -54,19 +65,21 @@ __device__ __forceinline__ void nb_tile_f32(const float* __restrict__ stage, int
             const float2 ms = h ? make_float2(M.z, M.w) : make_float2(M.x, M.y);
 #pragma unroll
             for (int t = 0; t < TI; ++t) {
-                const float2 dx = __fadd2_rn(xs, npos[t][0]);
-                const float2 dy = __fadd2_rn(ys, npos[t][1]);
+                const float2 dx = __fadd2_rn(xs, make_float2(npos[t][0], npos[t][0]));
+                const float2 dy = __fadd2_rn(ys, make_float2(npos[t][1], npos[t][1]));
                 float2 r2 = __fmul2_rn(dx, dx);
                 r2 = __ffma2_rn(dy, dy, r2);
                 float2 dz;
                 if (D == 3) {
-                    dz = __fadd2_rn(zs, npos[t][2]);
+                    dz = __fadd2_rn(zs, make_float2(npos[t][2], npos[t][2]));
                     r2 = __ffma2_rn(dz, dz, r2);
                 }
-                // hard cut-off (methods.cpp:119): pairs with r^2 < cutoff are DROPPED, which also
-                // removes the self pair and exact duplicates (r^2 = 0): rcp(+inf) = 0.
-                r2.x = (r2.x >= cutoff) ? r2.x : inf;
-                r2.y = (r2.y >= cutoff) ? r2.y : inf;
+                if (EXACT) {
+                    r2.x = (r2.x >= cutoff) ? r2.x : inf;
+                    r2.y = (r2.y >= cutoff) ? r2.y : inf;
+                } else {
+                    rmin = fminf(rmin, fminf(r2.x, r2.y));    // one FMNMX3
+                }
                 float2 inv;
                 inv.x = nb_rcp_f32(r2.x);
                 inv.y = nb_rcp_f32(r2.y);
@@ -78,11 +91,7 @@ __device__ __forceinline__ void nb_tile_f32(const float* __restrict__ stage, int
             }
         }
     }
-    // per-tile flush of the short FP32 partial sums into FP64
-#pragma unroll
-    for (int t = 0; t < TI; ++t)
-#pragma unroll
-        for (int d = 0; d < D; ++d) accd[t][d] += (double)(a[t][d].x + a[t][d].y);
+    return rmin;
 }
 
 // FP64: one tile against TI targets (pos holds the plain target coordinates).
@@ -156,6 +165,9 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
     }
     __syncthreads();
 
+    const float cutoff_f = (float)P.cutoff;
+    // redo threshold of the FP32 fast pass: the cut-off, but never 0 (r^2 = 0 must always redo)
+    const float cutoff_redo = fmaxf(cutoff_f, 1.0e-37f);
     const int total_units = P.n_itiles * (P.nseg0 + P.nseg1);
     unsigned kt = 0;                                 // tiles consumed by this CTA so far (ring position)
 
@@ -205,12 +217,12 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
 #pragma unroll
             for (int d = 0; d < 3; ++d) accd[t][d] = 0.0;
 
-        float2 npos[TI][3];
+        float npos[TI][3];
         if (!F64) {
 #pragma unroll
             for (int t = 0; t < TI; ++t)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) npos[t][d] = make_float2(-(float)tpos[t][d], -(float)tpos[t][d]);
+                for (int d = 0; d < 3; ++d) npos[t][d] = -(float)tpos[t][d];
         }
 
         for (int t = 0; t < ntl; ++t) {
@@ -231,8 +243,15 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
                 nb_tile_f64<D, TI, JS>(reinterpret_cast<const double*>(stage), part, P.cutoff,
                                        reinterpret_cast<const double(&)[TI][3]>(tpos), accd);
             } else {
-                nb_tile_f32<D, TI, JS>(reinterpret_cast<const float*>(stage), part, (float)P.cutoff, npos,
-                                       accd);
+                const float* fstage = reinterpret_cast<const float*>(stage);
+                float2 a[TI][3];
+                const float rmin = nb_tile_f32<D, TI, JS, false>(fstage, part, cutoff_f, npos, a);
+                if (!(rmin >= cutoff_redo)) nb_tile_f32<D, TI, JS, true>(fstage, part, cutoff_f, npos, a);
+                // per-tile flush of the short FP32 partial sums into FP64
+#pragma unroll
+                for (int tt = 0; tt < TI; ++tt)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) accd[tt][d] += (double)(a[tt][d].x + a[tt][d].y);
             }
             __syncwarp();
             if ((tid & 31) == 0) nb_mbar_arrive(&empty_bar[slot]);

@@ -73,6 +73,7 @@ class _Oracle:
         L.oracle_simulate.argtypes = [ctypes.c_int, sz, _dp, ctypes.c_double, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_int, ctypes.c_int]
         L.oracle_energy.argtypes = [ctypes.c_int, sz, _dp, ctypes.c_double, ctypes.c_double, _dp, _dp]
+        L.oracle_condition.argtypes = [ctypes.c_int, sz, _dp, ctypes.c_double, ctypes.c_double, _dp]
         L.oracle_accuracy_pct.argtypes = [ctypes.c_int, sz, _dp, _dp]
         L.oracle_accuracy_pct.restype = ctypes.c_double
         L.oracle_num_threads.restype = ctypes.c_int
@@ -139,6 +140,17 @@ def energy(bodies, G=G_REF, cutoff=CUTOFF_REF):
     if rc:
         raise RuntimeError(f"oracle energy rc={rc}")
     return ke.value, pe.value
+
+
+def condition(bodies, G=G_REF, cutoff=CUTOFF_REF):
+    """kappa_i = sum_j |f_ij| / |sum_j f_ij|: the summation condition number of each body's force."""
+    dim = _dim_of(bodies)
+    b = _as_bodies(bodies, dim)
+    out = np.ones(b.shape[0])
+    rc = _o().oracle_condition(dim, b.shape[0], _p(b), G, cutoff, _p(out))
+    if rc:
+        raise RuntimeError(f"oracle condition rc={rc}")
+    return out
 
 
 def accuracy_pct(forces_, reference):

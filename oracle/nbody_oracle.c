@@ -259,6 +259,36 @@ int oracle_energy(int D, size_t n, const double *bodies, double G, double cutoff
     return 0;
 }
 
+
+/*
+ * Summation condition number of each body's force (harness diagnostic, not in the reference):
+ *   kappa_i = sum_j ||f_ij||_2 / ||sum_j f_ij||_2   >= 1
+ * The forward error of ANY finite-precision evaluation of the row sum is bounded by
+ * ~ c * u * kappa_i (u = unit roundoff), so FP32-mode parity is stated relative to kappa_i.
+ */
+int oracle_condition(int D, size_t n, const double *bodies, double G, double cutoff, double *kappa)
+{
+    if (D != 2 && D != 3) return -1;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        double acc[3] = {0.0, 0.0, 0.0}, sum_abs = 0.0;
+        for (size_t j = 0; j < n; j++) {
+            double f[3], nf = 0.0;
+            if (i == j) continue;
+            if (!pair_force(D, POS(bodies, i, D), POS(bodies, j, D), MASS(bodies, i, D),
+                            MASS(bodies, j, D), G, cutoff, f))
+                continue;
+            for (int d = 0; d < D; d++) { acc[d] -= f[d]; nf += f[d] * f[d]; }
+            sum_abs += sqrt(nf);
+        }
+        double na = 0.0;
+        for (int d = 0; d < D; d++) na += acc[d] * acc[d];
+        na = sqrt(na);
+        kappa[i] = na > 0.0 ? sum_abs / na : (sum_abs > 0.0 ? INFINITY : 1.0);
+    }
+    return 0;
+}
+
 /* compute_accuracy_omp, utils.h:170-219: % of bodies whose every component is within
  * 1 % of the reference force (|ref| < 1e-20 -> absolute test |f| <= 1e-9). */
 double oracle_accuracy_pct(int D, size_t n, const double *forces, const double *ref)

@@ -12,7 +12,7 @@
 __device__ __forceinline__ float rcpf(float x) { float y; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
-enum { FFMA_S, FFMA2_REUSE, FFMA2_3DIST, FFMA2_SQ, FADD2_BC, FMUL2_SQ, MIX, MIX_NOCUT, DFMA_, DFMA_3DIST, MUFU_, FSEL_ };
+enum { FFMA_S, FFMA2_REUSE, FFMA2_3DIST, FFMA2_SQ, FADD2_BC, FMUL2_SQ, MIX, MIX_NOCUT, DFMA_, DFMA_3DIST, MUFU_, FSEL_, MIX_MIN, MIX_RCP4 };
 
 template <int MODE> __global__ void __launch_bounds__(256) k(float* out, unsigned long long* stamp, float a, float b) {
     float2 acc[NACC], x[NACC], y[NACC];
@@ -25,6 +25,7 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, unsigne
         dacc[i] = threadIdx.x + i; dx[i] = a + i * 1e-9; dy[i] = b + i * 1e-12;
     }
     const float2 a2 = make_float2(a, a * 1.0001f), b2 = make_float2(b, b * 0.9999f);
+    float rmin = 1e30f;
     __syncthreads();
     unsigned long long g0 = gtime(); long long t0 = clock64();
 #pragma unroll 1
@@ -41,15 +42,17 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, unsigne
             else if (MODE == DFMA_3DIST) dacc[i] = fma(dx[i], dy[i], dacc[i]);
             else if (MODE == MUFU_) acc[i].x = rcpf(acc[i].x);
             else if (MODE == FSEL_) { acc[i].x = acc[i].x >= a ? acc[i].x : b; acc[i].y = acc[i].y >= b ? acc[i].y : a; a += 1e-9f; }
-            else if (MODE == MIX || MODE == MIX_NOCUT) {
+            else if (MODE == MIX || MODE == MIX_NOCUT || MODE == MIX_MIN || MODE == MIX_RCP4) {
                 // one packed pair-chain of the force kernel per i: 3 FADD2, FMUL2, 2 FFMA2, [2 FSETP+2 FSEL], 2 MUFU,
                 // 2 FMUL2, 3 FFMA2  (11 FMA-pipe packed ops)
                 const float2 s0 = make_float2(a + it, b + it);
                 const float2 d0 = __fadd2_rn(s0, x[i]), d1 = __fadd2_rn(s0, y[i]), d2 = __fadd2_rn(a2, x[i]);
                 float2 r2 = __fmul2_rn(d0, d0); r2 = __ffma2_rn(d1, d1, r2); r2 = __ffma2_rn(d2, d2, r2);
                 if (MODE == MIX) { r2.x = r2.x >= b ? r2.x : 1e38f; r2.y = r2.y >= b ? r2.y : 1e38f; }
-                float2 inv = make_float2(rcpf(r2.x), rcpf(r2.y));
-                float2 s = __fmul2_rn(inv, inv); s = __fmul2_rn(s, b2);
+                if (MODE == MIX_MIN) rmin = fminf(rmin, fminf(r2.x, r2.y));
+                float2 s;
+                if (MODE == MIX_RCP4) { const float2 r4 = __fmul2_rn(r2, r2); s = make_float2(rcpf(r4.x), rcpf(r4.y)); s = __fmul2_rn(s, b2); }
+                else { float2 inv = make_float2(rcpf(r2.x), rcpf(r2.y)); s = __fmul2_rn(inv, inv); s = __fmul2_rn(s, b2); }
                 acc[i] = __ffma2_rn(s, d0, acc[i]);
                 dacc[i] = dacc[i];   // keep signature
                 x[i] = x[i];
@@ -62,7 +65,7 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, unsigne
     float s = 0; double ds = 0;
 #pragma unroll
     for (int i = 0; i < NACC; ++i) { s += acc[i].x + acc[i].y; ds += dacc[i]; }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s + (float)ds + a;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s + (float)ds + a + rmin;
     if (threadIdx.x == 0) { stamp[2 * blockIdx.x] = (unsigned long long)(t1 - t0); stamp[2 * blockIdx.x + 1] = g1 - g0; }
 }
 
@@ -91,7 +94,7 @@ template <int MODE> void run(const char* name, double lane_ops_per_inner, int ct
 }
 
 int main() {
-    for (int c : {1, 2, 4}) {
+    for (int c : {2, 4}) {
         run<FFMA_S>("FFMA scalar x2", 2, c);
         run<FFMA2_REUSE>("FFMA2 acc=acc*a+b (reuse)", 2, c);
         run<FFMA2_3DIST>("FFMA2 acc=x*y+acc (3 distinct)", 2, c);
@@ -100,6 +103,8 @@ int main() {
         run<FMUL2_SQ>("FMUL2 acc*=acc", 2, c);
         run<MIX>("pair chain (11 packed+2MUFU+4ALU)", 22, c);
         run<MIX_NOCUT>("pair chain no cut-off", 22, c);
+        run<MIX_MIN>("pair chain + FMNMX3 min", 22, c);
+        run<MIX_RCP4>("pair chain rcp(r2*r2), no cut", 22, c);
         run<DFMA_>("DFMA reuse", 1, c);
         run<DFMA_3DIST>("DFMA 3 distinct", 1, c);
         run<MUFU_>("MUFU.RCP", 1, c);
