@@ -1,0 +1,125 @@
+// methods_cuda.cpp -- C++ adapter: reference types in, libnb200 C ABI underneath.
+// See methods_cuda.h.  Mirrors the structure of the reference's methods.cpp (template
+// definitions + explicit instantiations for D = 2, 3: methods.cpp:453-466, :495-499).
+#include "methods_cuda.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "nb200.h"
+
+namespace {
+
+// The reference's compile-time constants: utils.h:21 (G) and methods.cpp:24 (dist_sq < 1e-10).
+constexpr double kG = 4.471e-21;
+constexpr double kCutoffR2 = 1e-10;
+
+struct Session {
+    nb200_ctx* ctx = nullptr;
+    int dim = 0;
+    std::size_t n = 0;
+    int precision = 0;
+    int gpus = 0;
+    double last_ms = 0.0;
+    ~Session() { reset(); }
+    void reset() {
+        if (ctx) nb200_destroy(ctx);
+        ctx = nullptr;
+    }
+};
+
+Session& session() {
+    static Session s;
+    return s;
+}
+std::mutex& session_mutex() {
+    static std::mutex m;
+    return m;
+}
+
+int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : fallback;
+}
+
+[[noreturn]] void raise(const char* what, int rc, const nb200_ctx* ctx) {
+    throw std::runtime_error(std::string("BruteForce_CUDA: ") + what + " failed (" + std::to_string(rc) +
+                             "): " + nb200_last_error(ctx));
+}
+
+// (re)creates the cached context when the problem shape changes
+nb200_ctx* acquire(int dim, std::size_t n) {
+    Session& s = session();
+    const int precision = env_int("NB200_PRECISION", NB200_FP64);
+    const int gpus = env_int("NB200_GPUS", 1);
+    if (s.ctx && s.dim == dim && s.n == n && s.precision == precision && s.gpus == gpus) return s.ctx;
+    s.reset();
+    const int rc = nb200_create(&s.ctx, dim, n, precision, gpus);
+    if (rc != NB200_OK) {
+        s.ctx = nullptr;
+        raise("nb200_create", rc, nullptr);
+    }
+    s.dim = dim;
+    s.n = n;
+    s.precision = precision;
+    s.gpus = gpus;
+    return s.ctx;
+}
+
+}  // namespace
+
+template <int D>
+std::vector<Vector<D>> brute_force_cuda_n_body(const std::vector<Body<D>>& bodies) {
+    static_assert(sizeof(Body<D>) == (2 * D + 1) * sizeof(double), "Body<D> must be the packed AoS of body.h");
+    static_assert(sizeof(Vector<D>) == D * sizeof(double), "Vector<D> must be D doubles (vector.h)");
+    std::lock_guard<std::mutex> lock(session_mutex());
+    const std::size_t n = bodies.size();
+    std::vector<Vector<D>> forces(n);          // zero-initialised like methods.cpp:9-15
+    if (n == 0) return forces;
+    nb200_ctx* ctx = acquire(D, n);
+    int rc = nb200_upload_aos(ctx, bodies.data(), sizeof(Body<D>));
+    if (rc != NB200_OK) raise("nb200_upload_aos", rc, ctx);
+    rc = nb200_forces(ctx, kG, kCutoffR2, reinterpret_cast<double*>(forces.data()));
+    if (rc != NB200_OK) raise("nb200_forces", rc, ctx);
+    nb200_last_elapsed_ms(ctx, &session().last_ms);
+    return forces;
+}
+
+template <int D>
+void brute_force_cuda_simulate(std::vector<Body<D>>& bodies, double dt, int steps) {
+    std::lock_guard<std::mutex> lock(session_mutex());
+    const std::size_t n = bodies.size();
+    if (n == 0 || steps <= 0) return;
+    nb200_ctx* ctx = acquire(D, n);
+    int rc = nb200_upload_aos(ctx, bodies.data(), sizeof(Body<D>));
+    if (rc != NB200_OK) raise("nb200_upload_aos", rc, ctx);
+    rc = nb200_step(ctx, kG, kCutoffR2, dt, steps);
+    if (rc != NB200_OK) raise("nb200_step", rc, ctx);
+    rc = nb200_download_aos(ctx, bodies.data(), sizeof(Body<D>));
+    if (rc != NB200_OK) raise("nb200_download_aos", rc, ctx);
+    nb200_last_elapsed_ms(ctx, &session().last_ms);
+}
+
+template <int D>
+void brute_force_cuda_warmup(std::size_t n) {
+    std::lock_guard<std::mutex> lock(session_mutex());
+    if (n) acquire(D, n);
+}
+
+double brute_force_cuda_last_kernel_ms() { return session().last_ms; }
+
+void brute_force_cuda_release() {
+    std::lock_guard<std::mutex> lock(session_mutex());
+    session().reset();
+}
+
+// Explicit instantiations for the two dimensions the suite supports (main.cpp:889-892).
+template std::vector<Vector<2>> brute_force_cuda_n_body<2>(const std::vector<Body<2>>& bodies);
+template std::vector<Vector<3>> brute_force_cuda_n_body<3>(const std::vector<Body<3>>& bodies);
+template void brute_force_cuda_simulate<2>(std::vector<Body<2>>& bodies, double dt, int steps);
+template void brute_force_cuda_simulate<3>(std::vector<Body<3>>& bodies, double dt, int steps);
+template void brute_force_cuda_warmup<2>(std::size_t n);
+template void brute_force_cuda_warmup<3>(std::size_t n);
