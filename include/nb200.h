@@ -115,6 +115,7 @@ long long nb200_launch_count(const nb200_ctx* ctx);
  *   "seg_tiles"   source tiles (of 256 bodies) per work unit
  *   "grid_mult"   persistent CTAs = grid_mult * (SMs * occupancy) / 16  (16 = exactly resident)
  *   "overlap"     1 = split each step into local/remote passes around the all-gather (default)
+ *   "trace"       1 = append a CUDA-event timeline of shard 0 to nb200_plan() after nb200_step
  * Returns NB200_EINVAL for an unknown key. */
 int nb200_set_option(nb200_ctx* ctx, const char* key, long value);
 

