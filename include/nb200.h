@@ -50,6 +50,7 @@ typedef struct nb200_ctx nb200_ctx;
 #define NB200_ENOMEM (-5)
 
 #define NB200_UNIQUE_ID_BYTES 128
+#define NB200_IPC_BYTES 256
 
 /* ---- lifetime --------------------------------------------------------------------------- */
 
@@ -66,6 +67,17 @@ int nb200_create(nb200_ctx** out, int dim, size_t n, int precision, int ngpus);
 int nb200_create_rank(nb200_ctx** out, int dim, size_t n, int precision, int device, int rank,
                       int world, const void* unique_id);
 int nb200_get_unique_id(void* unique_id_out);
+
+/* Fused NVLink exchange for rank contexts (the default whenever it is attached): instead of an
+ * all-gather after each step, the integrator epilogue stores the new source rows straight into
+ * every peer's next-step buffer over NVLink peer memory, and a per-pair flag publishes the step.
+ * Each rank exports one NB200_IPC_BYTES blob (CUDA IPC handles of its two source buffers and its
+ * flag array); the caller all-gathers the blobs in rank order (any transport) and every rank
+ * attaches all `world` of them.  Single-process contexts (nb200_create) wire this up themselves
+ * through CUDA peer access.  Needs world <= 8 and peer access between all GPUs; without it the
+ * context keeps using its NCCL communicator. */
+int nb200_ipc_export(nb200_ctx* ctx, void* blob_out);
+int nb200_ipc_attach(nb200_ctx* ctx, const void* blobs, int count);
 
 void nb200_destroy(nb200_ctx* ctx);
 
@@ -115,6 +127,7 @@ long long nb200_launch_count(const nb200_ctx* ctx);
  *   "seg_tiles"   source tiles (of 256 bodies) per work unit
  *   "grid_mult"   persistent CTAs = grid_mult * (SMs * occupancy) / 16  (16 = exactly resident)
  *   "overlap"     1 = split each step into local/remote passes around the all-gather (default)
+ *   "exchange"    1 = fused NVLink peer stores from the epilogue (default when attached), 0 = ncclAllGather
  *   "trace"       1 = append a CUDA-event timeline of shard 0 to nb200_plan() after nb200_step
  * Returns NB200_EINVAL for an unknown key. */
 int nb200_set_option(nb200_ctx* ctx, const char* key, long value);

@@ -82,6 +82,18 @@ class NBodyCuda:
         except Exception:
             pass
 
+    def ipc_export(self) -> bytes:
+        """This rank's CUDA IPC blob for the fused NVLink exchange (nb200_ipc_export)."""
+        buf = ctypes.create_string_buffer(_lib.IPC_BYTES)
+        self._check(self._lib.nb200_ipc_export(self._h, buf), "ipc_export")
+        return buf.raw
+
+    def ipc_attach(self, blobs: list[bytes]):
+        """Attach the blobs of ALL ranks, in rank order (nb200_ipc_attach)."""
+        joined = b"".join(blobs)
+        buf = ctypes.create_string_buffer(joined, len(joined))
+        self._check(self._lib.nb200_ipc_attach(self._h, buf, len(blobs)), "ipc_attach")
+
     def set_option(self, key: str, value: int):
         self._check(self._lib.nb200_set_option(self._h, key.encode(), int(value)), f"set_option({key})")
 

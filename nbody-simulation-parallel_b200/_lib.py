@@ -17,6 +17,7 @@ HEADER = os.path.join(ROOT, "include", "nb200.h")
 
 NB200_FP64, NB200_FP32 = 64, 32
 UNIQUE_ID_BYTES = 128
+IPC_BYTES = 256
 
 _c = ctypes
 _ctx_p = _c.c_void_p
@@ -28,6 +29,8 @@ SIGNATURES = {
     "nb200_create_rank": (_c.c_int, [_c.POINTER(_ctx_p), _c.c_int, _c.c_size_t, _c.c_int, _c.c_int,
                                      _c.c_int, _c.c_int, _c.c_void_p]),
     "nb200_get_unique_id": (_c.c_int, [_c.c_void_p]),
+    "nb200_ipc_export": (_c.c_int, [_ctx_p, _c.c_void_p]),
+    "nb200_ipc_attach": (_c.c_int, [_ctx_p, _c.c_void_p, _c.c_int]),
     "nb200_destroy": (None, [_ctx_p]),
     "nb200_upload_aos": (_c.c_int, [_ctx_p, _c.c_void_p, _c.c_size_t]),
     "nb200_download_aos": (_c.c_int, [_ctx_p, _c.c_void_p, _c.c_size_t]),

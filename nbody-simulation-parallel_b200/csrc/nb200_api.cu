@@ -136,7 +136,16 @@ struct Shard {
     unsigned *tile_done = nullptr, *sched = nullptr;
     ncclComm_t comm_nccl = nullptr;
     int sms = 0;
+    // fused NVLink exchange (peer stores from the epilogue + flag handshake)
+    unsigned long long* flags = nullptr;              // [2*kMaxWorldP2P]: step flags, then epoch flags, by writer rank
+    int n_peers = 0;
+    int peer_rank[NB_MAX_PEERS] = {0};
+    void* peer_src[2][NB_MAX_PEERS] = {{nullptr}};    // peers' source buffers, mapped into this device
+    unsigned long long* peer_flags[NB_MAX_PEERS] = {nullptr};
+    bool ipc_opened = false;                          // peer pointers came from cudaIpcOpenMemHandle
 };
+
+constexpr int kMaxWorldP2P = NB_MAX_PEERS + 1;
 
 }  // namespace
 
@@ -147,6 +156,7 @@ struct nb200_ctx {
     int world = 1;                // shards over all processes
     bool rank_mode = false;
     bool detached = false;        // rank context without a communicator (single-GPU test hook)
+    bool p2p_ready = false;       // peer pointers + flags of every peer are mapped
     long long ntiles = 0;         // source tiles incl. padding: world * tiles_per_shard
     long long tiles_per_shard = 0;
     long long nalloc = 0;         // bodies allocated in each source buffer
@@ -154,9 +164,13 @@ struct nb200_ctx {
     int cur = 0;                  // current source buffer
     bool uploaded = false;
     double pos_scale = 1.0, mass_scale = 1.0;
+    int exchange = 0;             // 0 = NCCL all-gather, 1 = peer stores fused into the epilogue
+    unsigned long long step_index = 0;   // steps issued since creation (the published flag value)
+    unsigned long long epoch_base = 0;   // step_index at the last upload
+    unsigned long long epoch = 0;        // uploads so far (published on the epoch flags)
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = 1, opt_trace = 0;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = 1, opt_trace = 0, opt_exchange = -1;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
@@ -225,6 +239,8 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
     CK(cudaMalloc(&s.energy, 2 * sizeof(double)));
     CK(cudaMalloc(&s.tile_done, (tp / 32 + 1) * sizeof(unsigned)));
     CK(cudaMemset(s.tile_done, 0, (tp / 32 + 1) * sizeof(unsigned)));
+    CK(cudaMalloc(&s.flags, 2 * kMaxWorldP2P * sizeof(unsigned long long)));
+    CK(cudaMemset(s.flags, 0, 2 * kMaxWorldP2P * sizeof(unsigned long long)));
     CK(cudaMalloc(&s.sched, 2 * sizeof(unsigned)));
     CK(cudaMemset(s.sched, 0, 2 * sizeof(unsigned)));
     // opt in to the dynamic shared memory of every variant once
@@ -240,6 +256,14 @@ void free_shard(Shard& s) {
     if (s.compute) cudaStreamSynchronize(s.compute);
     if (s.comm) cudaStreamSynchronize(s.comm);
     if (s.comm_nccl && nccl_api()->CommDestroy) nccl_api()->CommDestroy(s.comm_nccl);
+    if (s.ipc_opened) {
+        for (int p = 0; p < s.n_peers; ++p) {
+            cudaIpcCloseMemHandle(s.peer_src[0][p]);
+            cudaIpcCloseMemHandle(s.peer_src[1][p]);
+            cudaIpcCloseMemHandle(s.peer_flags[p]);
+        }
+    }
+    cudaFree(s.flags);
     for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
     cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
     cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.tile_done); cudaFree(s.sched);
@@ -346,8 +370,36 @@ struct Ranges {
 int nsegs(int b, int e, int seg) { return e > b ? (e - b + seg - 1) / seg : 0; }
 
 // launch one pass of the force kernel on shard s over the given source-tile ranges
+struct Handshake {
+    bool exchange = false;       // fused peer-store exchange: epilogue rows also go to the peers' next buffers
+    unsigned long long wait_step = 0, wait_epoch = 0, signal_step = 0;
+};
+
+struct PeerRanks {
+    int r[NB_MAX_PEERS];
+    explicit PeerRanks(const Shard& s) { for (int p = 0; p < NB_MAX_PEERS; ++p) r[p] = s.peer_rank[p]; }
+};
+
+// one warp: lane p spins until peer p has published step >= want_step and epoch >= want_epoch
+__global__ void nb_wait_flags_kernel(const unsigned long long* flags, int stride, int n_peers, PeerRanks pr,
+                                     unsigned long long want_step, unsigned long long want_epoch) {
+    const int p = threadIdx.x;
+    if (p < n_peers) {
+        while (nb_ld_acquire_sys(flags + pr.r[p]) < want_step) __nanosleep(500);
+        while (nb_ld_acquire_sys(flags + stride + pr.r[p]) < want_epoch) __nanosleep(500);
+    }
+}
+
+// publish this shard's epoch (upload count) on every peer's epoch flag
+__global__ void nb_publish_epoch_kernel(NbForceParams P, int stride, unsigned long long epoch) {
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int p = 0; p < P.n_peers; ++p) nb_st_release_sys(P.peer_flags[p] + stride + P.my_rank, epoch);
+    }
+}
+
 int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsigned units_per_itile,
-                int mode, double G, double cutoff, double dt, int cur) {
+                int mode, double G, double cutoff, double dt, int cur, const Handshake& hs = Handshake()) {
     NbForceParams P;
     memset(&P, 0, sizeof P);
     P.src = s.src[cur];
@@ -376,6 +428,20 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
     P.dt = dt;
     P.acc_scale = (ctx->pos_scale * ctx->pos_scale * ctx->pos_scale) / ctx->mass_scale;
     P.pos_scale = ctx->pos_scale;
+    P.my_flags = s.flags;
+    P.my_rank = s.rank;
+    P.wait_step = hs.wait_step;
+    P.wait_epoch = hs.wait_epoch;
+    P.signal_step = hs.signal_step;
+    P.flag_stride = kMaxWorldP2P;
+    if (hs.exchange) {
+        P.n_peers = s.n_peers;
+        for (int p = 0; p < s.n_peers; ++p) {
+            P.peer_next[p] = s.peer_src[cur ^ 1][p];
+            P.peer_flags[p] = s.peer_flags[p];
+            P.peer_rank[p] = s.peer_rank[p];
+        }
+    }
     if (P.nseg0 + P.nseg1 == 0) return NB200_OK;
     const Variant& V = kVariants[pl.variant];
     ForceKernel k = pick_kernel(ctx->dim, ctx->f64, pl.variant);
@@ -438,6 +504,8 @@ int init_common(nb200_ctx* ctx) {
 }
 
 
+int publish_epoch(nb200_ctx* ctx);
+
 // AoS staging image -> tile-planar sources (both buffers) + FP64 master state, on every shard
 int pack_sources(nb200_ctx* ctx) {
     const int D = ctx->dim;
@@ -461,7 +529,7 @@ int pack_sources(nb200_ctx* ctx) {
         CK(cudaStreamSynchronize(s.compute));
     }
     ctx->cur = 0;
-    return NB200_OK;
+    return publish_epoch(ctx);
 }
 
 // FP32 range guard: kept pairs reach 1/r'^4 <= 1/cutoff'^2, which must stay finite in FP32, so
@@ -478,6 +546,75 @@ int ensure_fp32_scale(nb200_ctx* ctx, double cutoff) {
     frexp(need, &ex);
     ctx->pos_scale = ldexp(1.0, ex);       // power of two >= need
     return pack_sources(ctx);
+}
+
+// single-process context: map every other shard's buffers through CUDA peer access
+int setup_peers_single_process(nb200_ctx* ctx) {
+    const int G = (int)ctx->shards.size();
+    if (G < 2 || G > kMaxWorldP2P) return NB200_OK;
+    for (int a = 0; a < G; ++a)
+        for (int b = 0; b < G; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->shards[a].device, ctx->shards[b].device));
+            if (!can) return NB200_OK;          // stay on NCCL
+        }
+    for (int a = 0; a < G; ++a) {
+        Shard& s = ctx->shards[a];
+        CK(cudaSetDevice(s.device));
+        s.n_peers = 0;
+        for (int b = 0; b < G; ++b) {
+            if (a == b) continue;
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctx->shards[b].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(ctx, NB200_ECUDA, "cudaDeviceEnablePeerAccess(%d->%d): %s", s.device, ctx->shards[b].device,
+                            cudaGetErrorString(e));
+            cudaGetLastError();
+            const int p = s.n_peers++;
+            s.peer_rank[p] = ctx->shards[b].rank;
+            s.peer_src[0][p] = ctx->shards[b].src[0];
+            s.peer_src[1][p] = ctx->shards[b].src[1];
+            s.peer_flags[p] = ctx->shards[b].flags;
+        }
+    }
+    ctx->p2p_ready = true;
+    ctx->exchange = 1;
+    return NB200_OK;
+}
+
+int ensure_nccl_single_process(nb200_ctx* ctx) {
+    if (ctx->rank_mode || ctx->shards.size() < 2 || ctx->shards[0].comm_nccl) return NB200_OK;
+    NcclApi* a = nccl_api();
+    if (!a->error.empty()) return fail(ctx, NB200_ENCCL, "%s", a->error.c_str());
+    const int G = (int)ctx->shards.size();
+    std::vector<ncclComm_t> comms(G);
+    std::vector<int> devs(G);
+    for (int g = 0; g < G; ++g) devs[g] = ctx->shards[g].device;
+    ncclResult_t r = a->CommInitAll(comms.data(), G, devs.data());
+    if (r != ncclSuccess) return fail(ctx, NB200_ENCCL, "ncclCommInitAll: %s", a->GetErrorString(r));
+    for (int g = 0; g < G; ++g) ctx->shards[g].comm_nccl = comms[g];
+    return NB200_OK;
+}
+
+// after a (re)pack: new epoch, published to the peers once the pack kernels are done
+int publish_epoch(nb200_ctx* ctx) {
+    ctx->epoch++;
+    ctx->epoch_base = ctx->step_index;
+    if (!ctx->p2p_ready) return NB200_OK;
+    for (Shard& s : ctx->shards) {
+        if (s.n_peers == 0) continue;
+        CK(cudaSetDevice(s.device));
+        NbForceParams P;
+        memset(&P, 0, sizeof P);
+        P.n_peers = s.n_peers;
+        P.my_rank = s.rank;
+        for (int p = 0; p < s.n_peers; ++p) P.peer_flags[p] = s.peer_flags[p];
+        nb_publish_epoch_kernel<<<1, 32, 0, s.compute>>>(P, kMaxWorldP2P, ctx->epoch);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        CK(cudaStreamSynchronize(s.compute));
+    }
+    return NB200_OK;
 }
 
 }  // namespace
@@ -511,6 +648,63 @@ int nb200_get_unique_id(void* out) {
     return NB200_OK;
 }
 
+
+int nb200_ipc_export(nb200_ctx* ctx, void* blob) {
+    if (!ctx || !blob) return NB200_EINVAL;
+    if (!ctx->rank_mode) return fail(ctx, NB200_ESTATE, "ipc export is for nb200_create_rank contexts");
+    Shard& s = ctx->shards[0];
+    CK(cudaSetDevice(s.device));
+    unsigned char* out = static_cast<unsigned char*>(blob);
+    memset(out, 0, NB200_IPC_BYTES);
+    static_assert(3 * sizeof(cudaIpcMemHandle_t) + 8 <= NB200_IPC_BYTES, "ipc blob size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, s.src[0])); memcpy(out, &h, sizeof h);
+    CK(cudaIpcGetMemHandle(&h, s.src[1])); memcpy(out + sizeof h, &h, sizeof h);
+    CK(cudaIpcGetMemHandle(&h, s.flags));  memcpy(out + 2 * sizeof h, &h, sizeof h);
+    const int rank = s.rank, world = ctx->world;
+    memcpy(out + 3 * sizeof h, &rank, 4);
+    memcpy(out + 3 * sizeof h + 4, &world, 4);
+    return NB200_OK;
+}
+
+int nb200_ipc_attach(nb200_ctx* ctx, const void* blobs, int count) {
+    if (!ctx || !blobs) return NB200_EINVAL;
+    if (!ctx->rank_mode) return fail(ctx, NB200_ESTATE, "ipc attach is for nb200_create_rank contexts");
+    if (count != ctx->world) return fail(ctx, NB200_EINVAL, "expected %d blobs, got %d", ctx->world, count);
+    if (ctx->world > kMaxWorldP2P) return fail(ctx, NB200_EINVAL, "peer-store exchange supports up to %d GPUs", kMaxWorldP2P);
+    if (ctx->uploaded && !ctx->pristine) return fail(ctx, NB200_ESTATE, "attach before the first step");
+    Shard& s = ctx->shards[0];
+    CK(cudaSetDevice(s.device));
+    const unsigned char* in = static_cast<const unsigned char*>(blobs);
+    s.n_peers = 0;
+    for (int r = 0; r < count; ++r) {
+        const unsigned char* b = in + (size_t)r * NB200_IPC_BYTES;
+        int brank = -1, bworld = -1;
+        memcpy(&brank, b + 3 * sizeof(cudaIpcMemHandle_t), 4);
+        memcpy(&bworld, b + 3 * sizeof(cudaIpcMemHandle_t) + 4, 4);
+        if (brank != r || bworld != ctx->world) return fail(ctx, NB200_EINVAL, "blob %d is from rank %d of %d", r, brank, bworld);
+        if (r == s.rank) continue;
+        cudaIpcMemHandle_t h;
+        const int p = s.n_peers;
+        memcpy(&h, b, sizeof h);
+        CK(cudaIpcOpenMemHandle(&s.peer_src[0][p], h, cudaIpcMemLazyEnablePeerAccess));
+        memcpy(&h, b + sizeof h, sizeof h);
+        CK(cudaIpcOpenMemHandle(&s.peer_src[1][p], h, cudaIpcMemLazyEnablePeerAccess));
+        memcpy(&h, b + 2 * sizeof h, sizeof h);
+        void* f = nullptr;
+        CK(cudaIpcOpenMemHandle(&f, h, cudaIpcMemLazyEnablePeerAccess));
+        s.peer_flags[p] = static_cast<unsigned long long*>(f);
+        s.peer_rank[p] = r;
+        s.n_peers++;
+    }
+    s.ipc_opened = true;
+    ctx->p2p_ready = true;
+    ctx->exchange = 1;
+    // the epoch of an earlier upload was not published to anybody: publish it now
+    if (ctx->uploaded) { ctx->epoch--; return publish_epoch(ctx); }
+    return NB200_OK;
+}
+
 int nb200_create(nb200_ctx** out, int dim, size_t n, int precision, int ngpus) {
     if (!out) return fail(nullptr, NB200_EINVAL, "null out pointer");
     *out = nullptr;
@@ -537,14 +731,9 @@ int nb200_create(nb200_ctx** out, int dim, size_t n, int precision, int ngpus) {
     for (int g = 0; g < ngpus; ++g) place_shard(ctx, ctx->shards[g], g, devs[g]);
     rc = init_common(ctx);
     if (rc == NB200_OK && ngpus > 1) {
-        NcclApi* a = nccl_api();
-        if (!a->error.empty()) rc = fail(ctx, NB200_ENCCL, "%s", a->error.c_str());
-        else {
-            std::vector<ncclComm_t> comms(ngpus);
-            ncclResult_t r = a->CommInitAll(comms.data(), ngpus, devs.data());
-            if (r != ncclSuccess) rc = fail(ctx, NB200_ENCCL, "ncclCommInitAll: %s", a->GetErrorString(r));
-            else for (int g = 0; g < ngpus; ++g) ctx->shards[g].comm_nccl = comms[g];
-        }
+        // preferred exchange: peer stores fused into the epilogue; NCCL (lazily initialised) otherwise
+        rc = setup_peers_single_process(ctx);
+        if (rc == NB200_OK && !ctx->p2p_ready) rc = ensure_nccl_single_process(ctx);
     }
     if (rc) {
         g_create_error = ctx->error;
@@ -620,6 +809,12 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);
     else if (!strcmp(key, "overlap")) ctx->opt_overlap = value != 0;
     else if (!strcmp(key, "trace")) ctx->opt_trace = value != 0;
+    else if (!strcmp(key, "exchange")) {
+        if (value == 1 && !ctx->p2p_ready) return fail(ctx, NB200_ESTATE, "peer-store exchange is not attached");
+        if (value == 0 && ctx->rank_mode && ctx->world > 1 && !ctx->detached && !ctx->shards[0].comm_nccl)
+            return fail(ctx, NB200_ESTATE, "no NCCL communicator in this context");
+        ctx->exchange = value != 0;
+    }
     else return fail(ctx, NB200_EINVAL, "unknown option '%s'", key);
     return NB200_OK;
 }
@@ -729,16 +924,24 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
         return fail(ctx, NB200_ESTATE, "detached shard (no communicator): only nsteps == 1 is defined");
     if (int rc0 = ensure_fp32_scale(ctx, cutoff_r2)) return rc0;
     if (nsteps > 0) ctx->pristine = false;
-    const bool split = ctx->world > 1 && ctx->opt_overlap;
     const bool multi = ctx->world > 1 && !ctx->detached;
-    NcclApi* nccl = multi ? nccl_api() : nullptr;
+    const bool p2p = multi && ctx->exchange == 1;          // rows pushed by the epilogue over NVLink
+    const bool use_nccl = multi && !p2p;
+    // local|remote split: with NCCL it hides the all-gather behind the local pass; with the fused
+    // peer-store exchange it lets a rank start on its own sources before its peers finish.
+    const bool split = ctx->world > 1 && ctx->opt_overlap;
+    if (use_nccl) { if (int rcn = ensure_nccl_single_process(ctx)) return rcn; }
+    NcclApi* nccl = use_nccl ? nccl_api() : nullptr;
+    if (use_nccl && !ctx->shards[0].comm_nccl) return fail(ctx, NB200_ESTATE, "no exchange attached (NCCL or peer stores)");
     std::vector<Plan> plans(ctx->shards.size());
     for (size_t i = 0; i < ctx->shards.size(); ++i) {
         CK(cudaSetDevice(ctx->shards[i].device));
         int rc = make_plan(ctx, ctx->shards[i], &plans[i]);
         if (rc) return rc;
     }
-    describe_plan(ctx, plans[0], split ? "step(local|gather|remote)" : "step");
+    describe_plan(ctx, plans[0], !multi ? (split ? "step(local|remote, detached)" : "step")
+                                 : p2p ? (split ? "step(local|remote, fused NVLink peer stores)" : "step(fused NVLink peer stores)")
+                                       : (split ? "step(local|ncclAllGather|remote)" : "step(ncclAllGather)"));
     for (auto& t : ctx->trace) cudaEventDestroy(t.second);
     ctx->trace.clear();
     for (Shard& s : ctx->shards) {
@@ -750,6 +953,16 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
     const size_t shard_elems = (size_t)ctx->tiles_per_shard * NB_TILE * (ctx->dim + 1);
     for (int step = 0; step < nsteps; ++step) {
         const int cur = ctx->cur, nxt = cur ^ 1;
+        const unsigned long long k = ++ctx->step_index;
+        Handshake hs_remote;                   // for the pass that reads remote rows and runs the epilogues
+        if (p2p) {
+            hs_remote.exchange = true;
+            hs_remote.wait_step = (k - 1 > ctx->epoch_base) ? k - 1 : 0;   // rows of step k-1, unless they are the upload
+            hs_remote.wait_epoch = ctx->epoch;                             // every peer finished (re)packing its buffers
+            hs_remote.signal_step = k;
+        }
+        Handshake hs_local;
+        hs_local.exchange = p2p;
         for (size_t i = 0; i < ctx->shards.size(); ++i) {
             Shard& s = ctx->shards[i];
             const Plan& pl = plans[i];
@@ -759,26 +972,26 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
             if (split) {
                 Ranges own = {(int)s.tile_lo, (int)s.tile_hi, 0, 0};
                 trace_mark(ctx, s, s.compute, "A>", step);
-                rc = launch_pass(ctx, s, pl, own, upi, 1, G, cutoff_r2, dt, cur);
+                rc = launch_pass(ctx, s, pl, own, upi, 1, G, cutoff_r2, dt, cur, hs_local);
                 if (rc) return rc;
                 trace_mark(ctx, s, s.compute, "A<", step);
-                CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
+                if (use_nccl) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
                 trace_mark(ctx, s, s.compute, "B>", step);
                 Ranges rest = {0, (int)s.tile_lo, (int)s.tile_hi, NT};
-                rc = launch_pass(ctx, s, pl, rest, upi, 1, G, cutoff_r2, dt, cur);
+                rc = launch_pass(ctx, s, pl, rest, upi, 1, G, cutoff_r2, dt, cur, hs_remote);
             } else {
-                CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
+                if (use_nccl) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
                 Ranges all = {0, NT, 0, 0};
-                rc = launch_pass(ctx, s, pl, all, upi, 1, G, cutoff_r2, dt, cur);
+                rc = launch_pass(ctx, s, pl, all, upi, 1, G, cutoff_r2, dt, cur, hs_remote);
             }
             if (rc) return rc;
             trace_mark(ctx, s, s.compute, "B<", step);
-            if (multi) {
+            if (use_nccl) {
                 CK(cudaEventRecord(s.ev_pass_done, s.compute));
                 CK(cudaStreamWaitEvent(s.comm, s.ev_pass_done, 0));
             }
         }
-        if (multi) {
+        if (use_nccl) {
             // in-place all-gather of the freshly integrated shards into the next source buffer
             if (ctx->shards.size() > 1) CKN(nccl->GroupStart());
             for (Shard& s : ctx->shards) {
@@ -799,7 +1012,15 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
     }
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
-        if (multi) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[ctx->cur], 0));
+        if (use_nccl) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[ctx->cur], 0));
+        if (p2p && nsteps > 0 && s.n_peers > 0) {
+            // the call returns (and its device time ends) only when every peer has published the last
+            // step: our source buffer is complete and no peer store into it is still in flight
+            nb_wait_flags_kernel<<<1, 32, 0, s.compute>>>(s.flags, kMaxWorldP2P, s.n_peers, PeerRanks(s), ctx->step_index, 0ull);
+            CK(cudaGetLastError());
+            ctx->launches++;
+            trace_mark(ctx, s, s.compute, "W<", nsteps - 1);
+        }
         CK(cudaEventRecord(s.ev_stop, s.compute));
     }
     int rc_t = finish_timing(ctx);

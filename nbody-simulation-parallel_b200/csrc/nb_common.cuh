@@ -12,6 +12,7 @@
 
 #define NB_TILE 256          // sources per tile (one TMA bulk copy)
 #define NB_STAGES 3          // TMA ring depth
+#define NB_MAX_PEERS 7       // other GPUs of one NVSwitch box whose source buffers a shard writes
 
 struct NbForceParams {
     const void* src;         // current tile-planar sources, all npad bodies (float or double)
@@ -38,6 +39,22 @@ struct NbForceParams {
     double dt;
     double acc_scale;        // S = acc * acc_scale      (undo the FP32 power-of-two scaling)
     double pos_scale;        // source = pos * pos_scale (FP32 path; 1.0 for FP64)
+    // ---- fused position exchange over NVLink peer memory (multi-GPU step mode)
+    // The integrator epilogue stores the new source rows of the own targets straight into every
+    // peer's NEXT buffer (P2P stores), so no separate all-gather runs.  Step completion is
+    // published with one flag per (writer, reader) pair: the last CTA of the pass that ran the
+    // epilogues release-stores signal_step into peer_flags[p][my_rank]; a pass that reads remote
+    // rows first acquires my_flags[r] >= wait_step for every peer r.
+    void* peer_next[NB_MAX_PEERS];                    // peers' next-step source buffers (peer-mapped)
+    unsigned long long* peer_flags[NB_MAX_PEERS];     // peers' flag arrays (peer-mapped), indexed by writer rank
+    unsigned long long* my_flags;                     // this shard's flag array, written by the peers
+    int peer_rank[NB_MAX_PEERS];
+    int n_peers;
+    int my_rank;
+    unsigned long long wait_step;                     // 0 = this pass reads no remote rows newer than the upload
+    unsigned long long wait_epoch;                    // peers must have finished this many uploads (repacks)
+    unsigned long long signal_step;                   // 0 = this pass publishes nothing
+    int flag_stride;                                  // epoch flags live at my_flags[flag_stride + rank]
 };
 
 // ------------------------------------------------------------------ mbarrier / TMA (sm_90+ PTX)
@@ -79,6 +96,16 @@ __device__ __forceinline__ void nb_tma_load_1d(void* smem_dst, const void* gmem_
             "r"(nb_smem_u32(smem_dst)),
         "l"(gmem_src), "r"(bytes), "r"(nb_smem_u32(bar))
         : "memory");
+}
+
+// system-scope flag accessors for the cross-GPU step handshake
+__device__ __forceinline__ unsigned long long nb_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void nb_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ float nb_rcp_f32(float x) {

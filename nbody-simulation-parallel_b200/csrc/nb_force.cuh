@@ -168,6 +168,17 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
     const float cutoff_f = (float)P.cutoff;
     // redo threshold of the FP32 fast pass: the cut-off, but never 0 (r^2 = 0 must always redo)
     const float cutoff_redo = fmaxf(cutoff_f, 1.0e-37f);
+    // cross-GPU handshake: this pass reads rows that the peers' epilogues of the previous step wrote
+    // into OUR source buffer over NVLink; wait until every peer has published that step.
+    if ((P.wait_step | P.wait_epoch) != 0ull && P.n_peers > 0) {
+        if (tid < P.n_peers) {
+            const unsigned long long* f = P.my_flags + P.peer_rank[tid];
+            while (nb_ld_acquire_sys(f) < P.wait_step) __nanosleep(200);
+            while (nb_ld_acquire_sys(f + P.flag_stride) < P.wait_epoch) __nanosleep(200);
+        }
+        __syncthreads();
+    }
+
     const int total_units = P.n_itiles * (P.nseg0 + P.nseg1);
     unsigned kt = 0;                                 // tiles consumed by this CTA so far (ring position)
 
@@ -311,10 +322,15 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
                         x += v * P.dt;                        // methods.cpp:448 (uses the NEW v)
                         P.vel[(size_t)d * P.tpad + li] = v;
                         P.pos[(size_t)d * P.tpad + li] = x;
-                        nb[d * NB_TILE] = (real)(x * P.pos_scale);
+                        const real xs = (real)(x * P.pos_scale);
+                        nb[d * NB_TILE] = xs;
+                        // fused all-gather: the same row goes to every peer's next buffer (P2P store)
+                        const size_t off = (size_t)(b / NB_TILE) * TILE_ELEMS + (b % NB_TILE) + (size_t)d * NB_TILE;
+                        for (int pr = 0; pr < P.n_peers; ++pr) static_cast<real*>(P.peer_next[pr])[off] = xs;
                     }
                 }
             }
+            if (P.n_peers > 0 && P.mode == 1) __threadfence_system();   // remote rows before the exit count
             if (tid == 0) P.tile_done[it] = 0u;
         }
     }
@@ -326,6 +342,11 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
             P.sched[0] = 0u;
             P.sched[1] = 0u;
             __threadfence();
+            if (P.signal_step != 0ull) {
+                // every CTA fenced its remote rows (system scope) before its exit count above
+                __threadfence_system();
+                for (int pr = 0; pr < P.n_peers; ++pr) nb_st_release_sys(P.peer_flags[pr] + P.my_rank, P.signal_step);
+            }
         }
     }
 }

@@ -46,8 +46,26 @@ def broadcast_bytes(blob: bytes | None, nbytes: int, src: int = 0) -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
-def create_rank_context(pkg, dim: int, n: int, precision: int, device: int | None = None):
-    """Build this rank's NBodyCuda context; the NCCL unique id comes from rank 0's libnb200."""
+def all_gather_bytes(blob: bytes) -> list[bytes]:
+    """All-gather equal-size byte strings over the default process group (gloo or nccl)."""
+    import torch
+    import torch.distributed as dist
+
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).clone().to(dev)
+    parts = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, mine)
+    return [bytes(p.cpu().numpy().tobytes()) for p in parts]
+
+
+def create_rank_context(pkg, dim: int, n: int, precision: int, device: int | None = None,
+                        exchange: str = "auto"):
+    """Build this rank's NBodyCuda context.
+
+    The NCCL unique id comes from rank 0's libnb200 and is broadcast here; then every rank exports
+    its CUDA IPC blob, the blobs are all-gathered, and the fused NVLink peer-store exchange is
+    attached (``exchange`` = "auto" | "p2p" | "nccl").  If any rank cannot attach (no peer access),
+    all ranks stay on the NCCL all-gather."""
     import ctypes
 
     import torch.distributed as dist
@@ -65,7 +83,24 @@ def create_rank_context(pkg, dim: int, n: int, precision: int, device: int | Non
         uid = broadcast_bytes(uid, pkg._lib.UNIQUE_ID_BYTES, src=0)
     if device is None:
         device = env_rank_world()[2]
-    return pkg.NBodyCuda(dim, n, precision, device=device, rank=rank, world=world, unique_id=uid)
+    ctx = pkg.NBodyCuda(dim, n, precision, device=device, rank=rank, world=world, unique_id=uid)
+    if world > 1 and exchange in ("auto", "p2p"):
+        import torch
+
+        blobs = all_gather_bytes(ctx.ipc_export())
+        ok = 1
+        try:
+            ctx.ipc_attach(blobs)
+        except pkg.NB200Error:
+            if exchange == "p2p":
+                raise
+            ok = 0
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([ok], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 0:
+            ctx.set_option("exchange", 0)
+    return ctx
 
 
 def assemble_rows(rows_full: np.ndarray, lo: int, hi: int) -> np.ndarray:

@@ -262,6 +262,8 @@ def _ngpu():
 @pytest.mark.parametrize("ngpus", [2, 4, 8])
 @pytest.mark.parametrize("prec", [64, 32])
 def test_single_process_multi_gpu_matches_one_gpu(pkg, ngpus, prec):
+    """Target-sharded steps over several GPUs of one box: the fused NVLink peer-store exchange
+    (default) and the NCCL all-gather, each with and without the local|remote split."""
     if _ngpu() < ngpus:
         pytest.skip(f"needs {ngpus} GPUs")
     n = 20000
@@ -270,7 +272,27 @@ def test_single_process_multi_gpu_matches_one_gpu(pkg, ngpus, prec):
     fg = pkg.brute_force_cuda_n_body(b, prec, ngpus=ngpus)
     assert rel(pkg, fg, f1).max() <= 1e-13
     a1 = pkg.brute_force_cuda_simulate(b, 1e-3, 10, prec)
-    ag = pkg.brute_force_cuda_simulate(b, 1e-3, 10, prec, ngpus=ngpus)
-    assert np.abs(ag - a1).max() <= 1e-10 * np.abs(a1).max()
-    ag2 = pkg.brute_force_cuda_simulate(b, 1e-3, 10, prec, ngpus=ngpus, options={"overlap": 0})
-    assert np.abs(ag2 - a1).max() <= 1e-10 * np.abs(a1).max()
+    for exchange in (1, 0):
+        for overlap in (1, 0):
+            ag = pkg.brute_force_cuda_simulate(b, 1e-3, 10, prec, ngpus=ngpus,
+                                               options={"exchange": exchange, "overlap": overlap})
+            err = np.abs(ag - a1).max() / np.abs(a1).max()
+            assert err <= 1e-10, f"exchange={exchange} overlap={overlap}: {err:.3e}"
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("overlap", [1, 0])
+def test_one_process_per_gpu_torchrun(exchange, overlap):
+    """The torchrun flavour (one rank per GPU, CUDA IPC handles all-gathered over torch.distributed)."""
+    import os
+    import subprocess
+    import sys
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29600 + (0 if exchange == "p2p" else 2) + overlap
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "tools", "mp_check.py"), "--exchange", exchange, "--overlap", str(overlap)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MP_CHECK" in r.stdout and " OK " in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
