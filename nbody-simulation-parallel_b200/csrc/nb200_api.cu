@@ -364,7 +364,8 @@ int make_plan(nb200_ctx* ctx, const Shard& s, Plan* out) {
 }
 
 struct Ranges {
-    int r0b, r0e, r1b, r1e;
+    int b[3], e[3];
+    Ranges(int b0, int e0, int b1 = 0, int e1 = 0, int b2 = 0, int e2 = 0) : b{b0, b1, b2}, e{e0, e1, e2} {}
 };
 
 int nsegs(int b, int e, int seg) { return e > b ? (e - b + seg - 1) / seg : 0; }
@@ -372,6 +373,7 @@ int nsegs(int b, int e, int seg) { return e > b ? (e - b + seg - 1) / seg : 0; }
 // launch one pass of the force kernel on shard s over the given source-tile ranges
 struct Handshake {
     bool exchange = false;       // fused peer-store exchange: epilogue rows also go to the peers' next buffers
+    bool lazy = false;           // range 0 = own rows only: handshake when a CTA first reaches a remote unit
     unsigned long long wait_step = 0, wait_epoch = 0, signal_step = 0;
 };
 
@@ -416,9 +418,14 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
     P.tpad = s.tpad;
     P.n_itiles = pl.n_itiles;
     P.seg_tiles = pl.seg_tiles;
-    P.r0_begin = rg.r0b; P.r0_end = rg.r0e; P.r1_begin = rg.r1b; P.r1_end = rg.r1e;
-    P.nseg0 = nsegs(rg.r0b, rg.r0e, pl.seg_tiles);
-    P.nseg1 = nsegs(rg.r1b, rg.r1e, pl.seg_tiles);
+    int nseg_total = 0;
+    for (int r = 0; r < 3; ++r) {
+        P.rng_begin[r] = rg.b[r];
+        P.rng_end[r] = rg.e[r];
+        P.rng_nseg[r] = nsegs(rg.b[r], rg.e[r], pl.seg_tiles);
+        nseg_total += P.rng_nseg[r];
+    }
+    P.lazy_wait = hs.lazy ? 1 : 0;
     P.units_per_itile = units_per_itile;
     P.mode = mode;
     P.G = G;
@@ -442,10 +449,10 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
             P.peer_rank[p] = s.peer_rank[p];
         }
     }
-    if (P.nseg0 + P.nseg1 == 0) return NB200_OK;
+    if (nseg_total == 0) return NB200_OK;
     const Variant& V = kVariants[pl.variant];
     ForceKernel k = pick_kernel(ctx->dim, ctx->f64, pl.variant);
-    const int units = pl.n_itiles * (P.nseg0 + P.nseg1);
+    const int units = pl.n_itiles * nseg_total;
     const int grid = std::min(pl.grid, units);
     k<<<grid, V.block, smem_bytes(ctx->dim, ctx->f64), s.compute>>>(P);
     CK(cudaGetLastError());
@@ -474,6 +481,7 @@ int trace_mark(nb200_ctx* ctx, const Shard& s, cudaStream_t st, const char* labe
     return NB200_OK;
 }
 
+// split = the own tile range is segmented separately from the two remote ranges
 int total_units_per_itile(const nb200_ctx* ctx, const Shard& s, const Plan& pl, bool split) {
     const int NT = (int)ctx->ntiles;
     if (!split) return nsegs(0, NT, pl.seg_tiles);
@@ -901,7 +909,7 @@ int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out)
         if (&s == &ctx->shards[0]) describe_plan(ctx, pl, "forces");
         CK(cudaStreamWaitEvent(s.compute, s.ev_gather[ctx->cur], 0));
         CK(cudaEventRecord(s.ev_start, s.compute));
-        Ranges all = {0, (int)ctx->ntiles, 0, 0};
+        Ranges all(0, (int)ctx->ntiles);
         rc = launch_pass(ctx, s, pl, all, (unsigned)total_units_per_itile(ctx, s, pl, false), 0, G, cutoff_r2, 0.0, ctx->cur);
         if (rc) return rc;
         CK(cudaEventRecord(s.ev_stop, s.compute));
@@ -940,7 +948,7 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
         if (rc) return rc;
     }
     describe_plan(ctx, plans[0], !multi ? (split ? "step(local|remote, detached)" : "step")
-                                 : p2p ? (split ? "step(local|remote, fused NVLink peer stores)" : "step(fused NVLink peer stores)")
+                                 : p2p ? (split ? "step(own rows first, fused NVLink peer stores)" : "step(fused NVLink peer stores)")
                                        : (split ? "step(local|ncclAllGather|remote)" : "step(ncclAllGather)"));
     for (auto& t : ctx->trace) cudaEventDestroy(t.second);
     ctx->trace.clear();
@@ -969,19 +977,27 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
             CK(cudaSetDevice(s.device));
             const unsigned upi = (unsigned)total_units_per_itile(ctx, s, pl, split);
             int rc;
-            if (split) {
-                Ranges own = {(int)s.tile_lo, (int)s.tile_hi, 0, 0};
+            if (split && use_nccl) {
+                // two launches around the all-gather event: own sources, then the other shards'
+                Ranges own((int)s.tile_lo, (int)s.tile_hi);
                 trace_mark(ctx, s, s.compute, "A>", step);
                 rc = launch_pass(ctx, s, pl, own, upi, 1, G, cutoff_r2, dt, cur, hs_local);
                 if (rc) return rc;
                 trace_mark(ctx, s, s.compute, "A<", step);
-                if (use_nccl) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
+                CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
                 trace_mark(ctx, s, s.compute, "B>", step);
-                Ranges rest = {0, (int)s.tile_lo, (int)s.tile_hi, NT};
+                Ranges rest(0, (int)s.tile_lo, (int)s.tile_hi, NT);
                 rc = launch_pass(ctx, s, pl, rest, upi, 1, G, cutoff_r2, dt, cur, hs_remote);
+            } else if (split) {
+                // ONE launch, own rows first; a CTA takes the peer handshake only when it reaches its
+                // first remote unit, so a rank that is ahead keeps computing on its own rows
+                Ranges own_first((int)s.tile_lo, (int)s.tile_hi, 0, (int)s.tile_lo, (int)s.tile_hi, NT);
+                Handshake hs = hs_remote;
+                hs.lazy = true;
+                rc = launch_pass(ctx, s, pl, own_first, upi, 1, G, cutoff_r2, dt, cur, hs);
             } else {
                 if (use_nccl) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
-                Ranges all = {0, NT, 0, 0};
+                Ranges all(0, NT);
                 rc = launch_pass(ctx, s, pl, all, upi, 1, G, cutoff_r2, dt, cur, hs_remote);
             }
             if (rc) return rc;

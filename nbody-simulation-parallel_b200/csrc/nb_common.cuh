@@ -29,9 +29,10 @@ struct NbForceParams {
     int tpad;                // padded own targets (multiple of the i-tile)
     int n_itiles;            // tpad / ITILE
     int seg_tiles;           // source tiles per unit
-    int r0_begin, r0_end;    // first source-tile range of this launch
-    int r1_begin, r1_end;    // second source-tile range (may be empty)
-    int nseg0, nseg1;        // segments per range
+    int rng_begin[3], rng_end[3];   // up to three source-tile ranges of this launch (range 0 first)
+    int rng_nseg[3];                // segments (work units per i-tile) in each range
+    int lazy_wait;                  // 1: range 0 holds only OWN rows; take the peer handshake when the
+                                    //    CTA first reaches a unit of range 1/2 (hides inter-GPU skew)
     unsigned units_per_itile;  // units that must finish (over ALL launches of the step) per i-tile
     int mode;                // 0 = forces, 1 = step (integrate in the epilogue)
     double G;                // gravitational constant (utils.h:21 in the reference)

@@ -170,16 +170,21 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
     const float cutoff_redo = fmaxf(cutoff_f, 1.0e-37f);
     // cross-GPU handshake: this pass reads rows that the peers' epilogues of the previous step wrote
     // into OUR source buffer over NVLink; wait until every peer has published that step.
-    if ((P.wait_step | P.wait_epoch) != 0ull && P.n_peers > 0) {
+    bool need_wait = (P.wait_step | P.wait_epoch) != 0ull && P.n_peers > 0;
+    auto peer_handshake = [&]() {
         if (tid < P.n_peers) {
             const unsigned long long* f = P.my_flags + P.peer_rank[tid];
             while (nb_ld_acquire_sys(f) < P.wait_step) __nanosleep(200);
             while (nb_ld_acquire_sys(f + P.flag_stride) < P.wait_epoch) __nanosleep(200);
         }
         __syncthreads();
+    };
+    if (need_wait && !P.lazy_wait) {
+        peer_handshake();
+        need_wait = false;
     }
 
-    const int total_units = P.n_itiles * (P.nseg0 + P.nseg1);
+    const int total_units = P.n_itiles * (P.rng_nseg[0] + P.rng_nseg[1] + P.rng_nseg[2]);
     unsigned kt = 0;                                 // tiles consumed by this CTA so far (ring position)
 
     for (;;) {
@@ -190,15 +195,16 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
         if (u >= total_units) break;
         const int it = u % P.n_itiles;
         const int seg = u / P.n_itiles;
-        int ts, te;
-        if (seg < P.nseg0) {
-            ts = P.r0_begin + seg * P.seg_tiles;
-            te = min(ts + P.seg_tiles, P.r0_end);
-        } else {
-            ts = P.r1_begin + (seg - P.nseg0) * P.seg_tiles;
-            te = min(ts + P.seg_tiles, P.r1_end);
-        }
+        int rsel = 0, sloc = seg;
+        if (sloc >= P.rng_nseg[0]) { sloc -= P.rng_nseg[0]; rsel = 1; }
+        if (rsel == 1 && sloc >= P.rng_nseg[1]) { sloc -= P.rng_nseg[1]; rsel = 2; }
+        const int ts = P.rng_begin[rsel] + sloc * P.seg_tiles;
+        const int te = min(ts + P.seg_tiles, P.rng_end[rsel]);
         const int ntl = te - ts;
+        if (need_wait && rsel != 0) {          // first remote unit of this CTA (u is CTA-uniform)
+            peer_handshake();
+            need_wait = false;
+        }
 
         // producer prologue: up to NB_STAGES-1 tiles in flight before the first wait
         if (tid == 0) {
