@@ -30,6 +30,8 @@ import time
 
 import numpy as np
 
+os.environ["NCCL_DEBUG"] = "WARN"   # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner off it
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
@@ -320,10 +322,10 @@ def run_product_arm(args) -> None:
         "vs_baseline": None, "dtype": "f32" if prec == 32 else "f64", "data": "synthetic",
         "config": {"workload": f"c5: brute-force 3D uniform cube, N={n}, fused force+integrate step, dt={DT}",
                    "n": n, "dim": DIM, "precision": prec,
-                   "parallelism": f"targets sharded over {world} GPU(s), per-step position all-gather",
+                   "parallelism": f"targets sharded over {world} GPU(s); new positions stored into the peers' buffers over NVLink by the integrator epilogue" if world > 1 else "1 GPU",
                    "l2": "flushed between timed steps (256 MiB write)", "plan": plan},
         "pipelined": {"value": round(pipelined, 2), "ms_per_step": round(pipe_ms / args.steps, 3),
-                      "note": "same K steps in one nb200_step call, no L2 flush, all-gather overlapped"},
+                      "note": "same K steps in one nb200_step call, no L2 flush"},
         "wall_s_timed_region": round(wall, 3),
         "clocks": clocks,
         "e2e": {"value": round(e2e_val, 2), "unit": "G interactions/s", "h2d_bytes_per_step": h2d,

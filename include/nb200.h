@@ -126,7 +126,10 @@ long long nb200_launch_count(const nb200_ctx* ctx);
  *   "variant"     index into the compiled (targets/thread, j-split, block) table, -1 = auto
  *   "seg_tiles"   source tiles (of 256 bodies) per work unit
  *   "grid_mult"   persistent CTAs = grid_mult * (SMs * occupancy) / 16  (16 = exactly resident)
- *   "overlap"     1 = split each step into local/remote passes around the all-gather (default)
+ *   "overlap"     1 = own source rows first (fused exchange: one launch, the peer handshake is taken
+ *                 when a CTA first needs remote rows; NCCL: local pass | all-gather | remote pass),
+ *                 0 = one pass over all sources after the handshake / all-gather, -1 = auto (default:
+ *                 1 with the fused exchange, 0 with NCCL)
  *   "exchange"    1 = fused NVLink peer stores from the epilogue (default when attached), 0 = ncclAllGather
  *   "trace"       1 = append a CUDA-event timeline of shard 0 to nb200_plan() after nb200_step
  * Returns NB200_EINVAL for an unknown key. */

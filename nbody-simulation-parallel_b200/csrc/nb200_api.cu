@@ -170,7 +170,7 @@ struct nb200_ctx {
     unsigned long long epoch = 0;        // uploads so far (published on the epoch flags)
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = 1, opt_trace = 0, opt_exchange = -1;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
@@ -815,7 +815,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "variant")) ctx->opt_variant = (value >= 0 && value < kNumVariants) ? (int)value : -1;
     else if (!strcmp(key, "seg_tiles")) ctx->opt_seg_tiles = (int)std::max(0L, value);
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);
-    else if (!strcmp(key, "overlap")) ctx->opt_overlap = value != 0;
+    else if (!strcmp(key, "overlap")) ctx->opt_overlap = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "trace")) ctx->opt_trace = value != 0;
     else if (!strcmp(key, "exchange")) {
         if (value == 1 && !ctx->p2p_ready) return fail(ctx, NB200_ESTATE, "peer-store exchange is not attached");
@@ -937,7 +937,9 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
     const bool use_nccl = multi && !p2p;
     // local|remote split: with NCCL it hides the all-gather behind the local pass; with the fused
     // peer-store exchange it lets a rank start on its own sources before its peers finish.
-    const bool split = ctx->world > 1 && ctx->opt_overlap;
+    // auto: own-rows-first for the fused exchange and for detached shards; no split around NCCL (its
+    // kernels spin on SMs next to our persistent CTAs -- measured slower than exposing the gather)
+    const bool split = ctx->world > 1 && (ctx->opt_overlap < 0 ? !use_nccl : ctx->opt_overlap != 0);
     if (use_nccl) { if (int rcn = ensure_nccl_single_process(ctx)) return rcn; }
     NcclApi* nccl = use_nccl ? nccl_api() : nullptr;
     if (use_nccl && !ctx->shards[0].comm_nccl) return fail(ctx, NB200_ESTATE, "no exchange attached (NCCL or peer stores)");
