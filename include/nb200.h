@@ -97,7 +97,11 @@ int nb200_shard_range(const nb200_ctx* ctx, size_t* lo, size_t* hi);
 
 /* ---- the hot path ----------------------------------------------------------------------- */
 
-/* One force evaluation at the uploaded positions.  forces_out = n*D doubles (Vector<D> layout,
+/* cutoff_r2: pairs with r^2 < cutoff_r2 are dropped (methods.cpp:24 hard-codes 1e-10).  Values below
+ * 1e-20 are clamped to 1e-20: Vector<D>::normalized() already zeroes every pair with r < 1e-10
+ * (vector.h:95), so the reference cannot express a smaller cut-off either.
+ *
+ * One force evaluation at the uploaded positions.  forces_out = n*D doubles (Vector<D> layout,
  * body order); rank contexts fill rows [lo,hi) only.  Does not change the state. */
 int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out);
 

@@ -99,18 +99,23 @@ constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 typedef void (*ForceKernel)(const NbForceParams);
 
-template <int D, bool F64> ForceKernel kernel_for(int v) {
+template <int D, bool F64, bool FLAGS> ForceKernel kernel_for(int v) {
     switch (v) {
-        case 0: return nb_force_kernel<D, F64, 4, 1, 256>;
-        case 1: return nb_force_kernel<D, F64, 2, 1, 256>;
-        case 2: return nb_force_kernel<D, F64, 4, 4, 256>;
-        case 3: return nb_force_kernel<D, F64, 2, 4, 128>;
-        default: return nb_force_kernel<D, F64, 2, 8, 128>;
+        case 0: return nb_force_kernel<D, F64, 4, 1, 256, FLAGS>;
+        case 1: return nb_force_kernel<D, F64, 2, 1, 256, FLAGS>;
+        case 2: return nb_force_kernel<D, F64, 4, 4, 256, FLAGS>;
+        case 3: return nb_force_kernel<D, F64, 2, 4, 128, FLAGS>;
+        default: return nb_force_kernel<D, F64, 2, 8, 128, FLAGS>;
     }
 }
-ForceKernel pick_kernel(int dim, bool f64, int v) {
-    if (dim == 3) return f64 ? kernel_for<3, true>(v) : kernel_for<3, false>(v);
-    return f64 ? kernel_for<2, true>(v) : kernel_for<2, false>(v);
+// flags = the close-pair pre-pass ran and P.suspect is valid (NB_PLAIN / NB_EXACT per warp and tile)
+ForceKernel pick_kernel(int dim, bool f64, int v, bool flags = false) {
+    if (flags) {
+        if (dim == 3) return f64 ? kernel_for<3, true, true>(v) : kernel_for<3, false, true>(v);
+        return f64 ? kernel_for<2, true, true>(v) : kernel_for<2, false, true>(v);
+    }
+    if (dim == 3) return f64 ? kernel_for<3, true, false>(v) : kernel_for<3, false, false>(v);
+    return f64 ? kernel_for<2, true, false>(v) : kernel_for<2, false, false>(v);
 }
 
 size_t smem_bytes(int dim, bool f64) {
@@ -136,6 +141,11 @@ struct Shard {
     unsigned *tile_done = nullptr, *sched = nullptr;
     ncclComm_t comm_nccl = nullptr;
     int sms = 0;
+    // close-pair pre-pass
+    unsigned long long* grid_keys = nullptr;
+    unsigned* grid_counts = nullptr;
+    unsigned grid_cap = 0;
+    unsigned char* suspect = nullptr;                 // [tpad]
     // fused NVLink exchange (peer stores from the epilogue + flag handshake)
     unsigned long long* flags = nullptr;              // [2*kMaxWorldP2P]: step flags, then epoch flags, by writer rank
     int n_peers = 0;
@@ -164,13 +174,14 @@ struct nb200_ctx {
     int cur = 0;                  // current source buffer
     bool uploaded = false;
     double pos_scale = 1.0, mass_scale = 1.0;
+    double xmax = 1.0;            // max |coordinate| at upload (cell size of the close-pair grid when cutoff = 0)
     int exchange = 0;             // 0 = NCCL all-gather, 1 = peer stores fused into the epilogue
     unsigned long long step_index = 0;   // steps issued since creation (the published flag value)
     unsigned long long epoch_base = 0;   // step_index at the last upload
     unsigned long long epoch = 0;        // uploads so far (published on the epoch flags)
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
@@ -239,15 +250,25 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
     CK(cudaMalloc(&s.energy, 2 * sizeof(double)));
     CK(cudaMalloc(&s.tile_done, (tp / 32 + 1) * sizeof(unsigned)));
     CK(cudaMemset(s.tile_done, 0, (tp / 32 + 1) * sizeof(unsigned)));
+    {
+        unsigned cap = 1024;
+        while ((long long)cap < 2 * ctx->ntiles * NB_TILE) cap <<= 1;
+        s.grid_cap = cap;
+        CK(cudaMalloc(&s.grid_keys, (size_t)cap * sizeof(unsigned long long)));
+        CK(cudaMalloc(&s.grid_counts, (size_t)cap * sizeof(unsigned)));
+        CK(cudaMalloc(&s.suspect, tp));
+        CK(cudaMemset(s.suspect, 1, tp));
+    }
     CK(cudaMalloc(&s.flags, 2 * kMaxWorldP2P * sizeof(unsigned long long)));
     CK(cudaMemset(s.flags, 0, 2 * kMaxWorldP2P * sizeof(unsigned long long)));
     CK(cudaMalloc(&s.sched, 2 * sizeof(unsigned)));
     CK(cudaMemset(s.sched, 0, 2 * sizeof(unsigned)));
     // opt in to the dynamic shared memory of every variant once
     for (int v = 0; v < kNumVariants; ++v)
-        CK(cudaFuncSetAttribute((const void*)pick_kernel(D, ctx->f64, v),
-                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem_bytes(D, ctx->f64)));
+        for (int fl = 0; fl < 2; ++fl)
+            CK(cudaFuncSetAttribute((const void*)pick_kernel(D, ctx->f64, v, fl != 0),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_bytes(D, ctx->f64)));
     return NB200_OK;
 }
 
@@ -264,6 +285,7 @@ void free_shard(Shard& s) {
         }
     }
     cudaFree(s.flags);
+    cudaFree(s.grid_keys); cudaFree(s.grid_counts); cudaFree(s.suspect);
     for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
     cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
     cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.tile_done); cudaFree(s.sched);
@@ -312,16 +334,25 @@ struct Plan {
     int seg_tiles;
     int grid;
     int n_itiles;
+    bool flags;       // close-pair pre-pass + NB_PLAIN/NB_EXACT kernels instead of the tracked pass
 };
+
+// the pre-pass costs three small launches per step: worth it once a step is >~ 1 ms
+bool use_detect(const nb200_ctx* ctx) {
+    if (ctx->opt_detect >= 0) return ctx->opt_detect != 0;
+    return ctx->n >= 65536;
+}
 
 int make_plan(nb200_ctx* ctx, const Shard& s, Plan* out) {
     const int D = ctx->dim;
     const long long NT = ctx->ntiles;
     int occ = 1;
+    const bool flags = use_detect(ctx);
+    out->flags = flags;
     auto resident = [&](int v, int* grid) -> int {
         int nb = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &nb, (const void*)pick_kernel(D, ctx->f64, v), kVariants[v].block, smem_bytes(D, ctx->f64));
+            &nb, (const void*)pick_kernel(D, ctx->f64, v, flags), kVariants[v].block, smem_bytes(D, ctx->f64));
         if (e != cudaSuccess) return -1;
         *grid = std::max(1, nb) * s.sms;
         return nb;
@@ -371,6 +402,36 @@ struct Ranges {
 int nsegs(int b, int e, int seg) { return e > b ? (e - b + seg - 1) / seg : 0; }
 
 // launch one pass of the force kernel on shard s over the given source-tile ranges
+// close-pair pre-pass on the shard's compute stream: hash-grid insert of every source, then the
+// suspect flag of every own (padded) target.  Reads src[cur], so it runs after the peer handshake.
+int launch_detect(nb200_ctx* ctx, Shard& s, double cutoff, int cur) {
+    const int D = ctx->dim;
+    const long long nbodies = ctx->ntiles * NB_TILE;
+    const double cs = cutoff * ctx->pos_scale * ctx->pos_scale;
+    NbGrid g;
+    g.keys = s.grid_keys;
+    g.counts = s.grid_counts;
+    g.mask = s.grid_cap - 1;
+    // cell edge >= sqrt(cutoff) * 1.001; with no cut-off only exact duplicates matter: any tiny cell does,
+    // but keep cell indices far inside the int64 range
+    const double h = cs > 0.0 ? sqrt(cs) * 1.001 : ldexp(ctx->xmax * ctx->pos_scale, -40);
+    g.inv_h = 1.0 / h;
+    CK(cudaMemsetAsync(s.grid_keys, 0xFF, (size_t)s.grid_cap * sizeof(unsigned long long), s.compute));
+    CK(cudaMemsetAsync(s.grid_counts, 0, (size_t)s.grid_cap * sizeof(unsigned), s.compute));
+    const int threads = 256;
+    const int bi = (int)((nbodies + threads - 1) / threads), bq = (s.tpad + threads - 1) / threads;
+#define NB_GRID(DD, RR)                                                                                    \
+    nb_grid_insert_kernel<DD, RR><<<bi, threads, 0, s.compute>>>((const RR*)s.src[cur], nbodies, g);       \
+    nb_grid_query_kernel<DD, RR><<<bq, threads, 0, s.compute>>>((const RR*)s.src[cur], s.tgt_base, s.tpad, \
+                                                                 nbodies, g, s.suspect)
+    if (D == 3) { if (ctx->f64) { NB_GRID(3, double); } else { NB_GRID(3, float); } }
+    else        { if (ctx->f64) { NB_GRID(2, double); } else { NB_GRID(2, float); } }
+#undef NB_GRID
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    return NB200_OK;
+}
+
 struct Handshake {
     bool exchange = false;       // fused peer-store exchange: epilogue rows also go to the peers' next buffers
     bool lazy = false;           // range 0 = own rows only: handshake when a CTA first reaches a remote unit
@@ -413,6 +474,7 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
     P.vel = s.vel;
     P.mass = s.mass;
     P.forces = s.forces;
+    P.suspect = pl.flags ? s.suspect : nullptr;
     P.tgt_base = s.tgt_base;
     P.n_local = s.n_local;
     P.tpad = s.tpad;
@@ -451,7 +513,7 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
     }
     if (nseg_total == 0) return NB200_OK;
     const Variant& V = kVariants[pl.variant];
-    ForceKernel k = pick_kernel(ctx->dim, ctx->f64, pl.variant);
+    ForceKernel k = pick_kernel(ctx->dim, ctx->f64, pl.variant, pl.flags);
     const int units = pl.n_itiles * nseg_total;
     const int grid = std::min(pl.grid, units);
     k<<<grid, V.block, smem_bytes(ctx->dim, ctx->f64), s.compute>>>(P);
@@ -465,9 +527,10 @@ void describe_plan(nb200_ctx* ctx, const Plan& pl, const char* what) {
     const Variant& V = kVariants[pl.variant];
     snprintf(buf, sizeof buf,
              "%s: fp%d dim=%d n=%zu shards=%d variant=%d(TI=%d,JS=%d,block=%d,itile=%d) seg_tiles=%d "
-             "i-tiles=%d grid=%d tiles=%lld",
+             "i-tiles=%d grid=%d tiles=%lld cutoff=%s",
              what, ctx->f64 ? 64 : 32, ctx->dim, ctx->n, ctx->world, pl.variant, V.ti, V.js, V.block, V.itile(),
-             pl.seg_tiles, pl.n_itiles, pl.grid, ctx->ntiles);
+             pl.seg_tiles, pl.n_itiles, pl.grid, ctx->ntiles,
+             pl.flags ? "grid-prepass(plain|exact)" : (ctx->f64 ? "exact" : "tracked+redo"));
     ctx->plan = buf;
 }
 
@@ -817,6 +880,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);
     else if (!strcmp(key, "overlap")) ctx->opt_overlap = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "trace")) ctx->opt_trace = value != 0;
+    else if (!strcmp(key, "detect")) ctx->opt_detect = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "exchange")) {
         if (value == 1 && !ctx->p2p_ready) return fail(ctx, NB200_ESTATE, "peer-store exchange is not attached");
         if (value == 0 && ctx->rank_mode && ctx->world > 1 && !ctx->detached && !ctx->shards[0].comm_nccl)
@@ -838,7 +902,8 @@ int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
     const size_t sd = stride / sizeof(double);
     // FP32 pair math runs on power-of-two-scaled sources (exact): |x'| <= 1, m' <= 1
     ctx->pos_scale = ctx->mass_scale = 1.0;
-    if (!ctx->f64 && ctx->n) {
+    ctx->xmax = 1.0;
+    if (ctx->n) {
         double xmax = 0.0, mmax = 0.0;
         const double* p = static_cast<const double*>(bodies);
         for (size_t i = 0; i < ctx->n; ++i) {
@@ -847,8 +912,11 @@ int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
             mmax = std::max(mmax, fabs(r[2 * D]));
         }
         int ex = 0;
-        if (xmax > 0 && isfinite(xmax)) { frexp(xmax, &ex); ctx->pos_scale = ldexp(1.0, -ex); }
-        if (mmax > 0 && isfinite(mmax)) { frexp(mmax, &ex); ctx->mass_scale = ldexp(1.0, -ex); }
+        if (xmax > 0 && isfinite(xmax)) ctx->xmax = xmax;
+        if (!ctx->f64) {
+            if (xmax > 0 && isfinite(xmax)) { frexp(xmax, &ex); ctx->pos_scale = ldexp(1.0, -ex); }
+            if (mmax > 0 && isfinite(mmax)) { frexp(mmax, &ex); ctx->mass_scale = ldexp(1.0, -ex); }
+        }
     }
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
@@ -895,8 +963,13 @@ int nb200_download_aos(nb200_ctx* ctx, void* bodies, size_t stride) {
     return NB200_OK;
 }
 
+// Vector<D>::normalized() zeroes the direction of any pair with r < 1e-10 (vector.h:95), so a
+// cut-off below 1e-20 on r^2 cannot be expressed by the reference: clamp to that guard.
+static inline double effective_cutoff(double c) { return c > 1e-20 ? c : 1e-20; }
+
 int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out) {
     if (!ctx) return NB200_EINVAL;
+    cutoff_r2 = effective_cutoff(cutoff_r2);
     if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "forces before upload");
     if (ctx->n && !forces_out) return fail(ctx, NB200_EINVAL, "null forces_out");
     const int D = ctx->dim;
@@ -909,6 +982,7 @@ int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out)
         if (&s == &ctx->shards[0]) describe_plan(ctx, pl, "forces");
         CK(cudaStreamWaitEvent(s.compute, s.ev_gather[ctx->cur], 0));
         CK(cudaEventRecord(s.ev_start, s.compute));
+        if (pl.flags) { if (int rcd = launch_detect(ctx, s, cutoff_r2, ctx->cur)) return rcd; }
         Ranges all(0, (int)ctx->ntiles);
         rc = launch_pass(ctx, s, pl, all, (unsigned)total_units_per_itile(ctx, s, pl, false), 0, G, cutoff_r2, 0.0, ctx->cur);
         if (rc) return rc;
@@ -926,6 +1000,7 @@ int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out)
 
 int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps) {
     if (!ctx) return NB200_EINVAL;
+    cutoff_r2 = effective_cutoff(cutoff_r2);
     if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "step before upload");
     if (nsteps < 0) return fail(ctx, NB200_EINVAL, "nsteps < 0");
     if (ctx->detached && nsteps > 1)
@@ -979,6 +1054,18 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
             CK(cudaSetDevice(s.device));
             const unsigned upi = (unsigned)total_units_per_itile(ctx, s, pl, split);
             int rc;
+            if (pl.flags) {
+                // the pre-pass reads every source row of this step: take the exchange handshake first
+                if (use_nccl) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
+                if (p2p && s.n_peers > 0 && (hs_remote.wait_step | hs_remote.wait_epoch)) {
+                    nb_wait_flags_kernel<<<1, 32, 0, s.compute>>>(s.flags, kMaxWorldP2P, s.n_peers, PeerRanks(s),
+                                                                  hs_remote.wait_step, hs_remote.wait_epoch);
+                    CK(cudaGetLastError());
+                    ctx->launches++;
+                }
+                rc = launch_detect(ctx, s, cutoff_r2, cur);
+                if (rc) return rc;
+            }
             if (split && use_nccl) {
                 // two launches around the all-gather event: own sources, then the other shards'
                 Ranges own((int)s.tile_lo, (int)s.tile_hi);
@@ -1060,6 +1147,7 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
 int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, double* potential) {
     if (!ctx || !kinetic || !potential) return NB200_EINVAL;
     if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "energy before upload");
+    cutoff_r2 = effective_cutoff(cutoff_r2);
     double ke = 0.0, pe = 0.0;
     const double cs = cutoff_r2 * ctx->pos_scale * ctx->pos_scale;
     for (Shard& s : ctx->shards) {

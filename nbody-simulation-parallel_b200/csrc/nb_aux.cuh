@@ -129,3 +129,73 @@ __global__ void __launch_bounds__(256) nb_energy_kernel(const real* __restrict__
         atomicAdd(&out[1], c);
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Close-pair pre-pass (O(N)): lets the force kernel drop ALL per-pair cut-off work (NB_PLAIN).
+// A uniform hash grid with cell edge h >= sqrt(cutoff) * 1.001 counts the bodies per cell; a
+// target is "suspect" when the 3^D cells around it hold any body besides itself.  Every pair
+// with r^2 < cutoff (as the kernel computes it: FP32 rounding moves r^2 by < 1e-6 relative)
+// lies in adjacent cells, so both of its bodies are flagged; false positives only cost speed.
+struct NbGrid {
+    unsigned long long* keys;   // open addressing, linear probing; ~0ull = empty
+    unsigned* counts;
+    unsigned mask;              // capacity - 1 (power of two)
+    double inv_h;               // 1 / cell edge, in source units
+};
+
+__device__ __forceinline__ unsigned long long nb_cell_key(long long cx, long long cy, long long cz) {
+    unsigned long long k = (unsigned long long)cx * 0x9E3779B97F4A7C15ull;
+    k ^= ((unsigned long long)cy * 0xC2B2AE3D27D4EB4Full) + 0x165667B19E3779F9ull + (k << 6) + (k >> 2);
+    k ^= ((unsigned long long)cz * 0xD6E8FEB86659FD93ull) + 0x9E3779B97F4A7C15ull + (k << 6) + (k >> 2);
+    return k == ~0ull ? 0ull : k;
+}
+__device__ __forceinline__ unsigned nb_slot_of(unsigned long long key, unsigned mask) {
+    return (unsigned)((key * 0xFF51AFD7ED558CCDull) >> 32) & mask;
+}
+
+template <int D, typename real>
+__global__ void nb_grid_insert_kernel(const real* __restrict__ src, long long nbodies, NbGrid g) {
+    constexpr int NP = D + 1;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbodies) return;
+    const real* tb = src + (size_t)(b / NB_TILE) * (NB_TILE * NP) + (b % NB_TILE);
+    long long c[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < D; ++d) c[d] = (long long)floor((double)tb[d * NB_TILE] * g.inv_h);
+    const unsigned long long key = nb_cell_key(c[0], c[1], c[2]);
+    unsigned slot = nb_slot_of(key, g.mask);
+    for (;;) {
+        const unsigned long long prev = atomicCAS(&g.keys[slot], ~0ull, key);
+        if (prev == ~0ull || prev == key) break;
+        slot = (slot + 1) & g.mask;
+    }
+    atomicAdd(&g.counts[slot], 1u);
+}
+
+template <int D, typename real>
+__global__ void nb_grid_query_kernel(const real* __restrict__ src, long long tgt_base, int tpad,
+                                     long long nbodies, NbGrid g, unsigned char* __restrict__ suspect) {
+    constexpr int NP = D + 1;
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= tpad) return;
+    const long long b = tgt_base + li;
+    if (b >= nbodies) { suspect[li] = 1; return; }      // slack rows past the last source tile
+    const real* tb = src + (size_t)(b / NB_TILE) * (NB_TILE * NP) + (b % NB_TILE);
+    long long c[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < D; ++d) c[d] = (long long)floor((double)tb[d * NB_TILE] * g.inv_h);
+    unsigned total = 0;
+    for (int dz = (D == 3 ? -1 : 0); dz <= (D == 3 ? 1 : 0); ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const unsigned long long key = nb_cell_key(c[0] + dx, c[1] + dy, c[2] + dz);
+                unsigned slot = nb_slot_of(key, g.mask);
+                for (;;) {
+                    const unsigned long long k = g.keys[slot];
+                    if (k == key) { total += g.counts[slot]; break; }
+                    if (k == ~0ull) break;
+                    slot = (slot + 1) & g.mask;
+                }
+            }
+    suspect[li] = total > 1u;                             // anything besides the body itself
+}

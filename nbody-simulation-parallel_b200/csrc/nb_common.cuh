@@ -24,6 +24,7 @@ struct NbForceParams {
     double* vel;             // [D][tpad] master velocities
     const double* mass;      // [tpad]    master masses
     double* forces;          // [n_local][D] AoS Vector<D> output (forces mode)
+    const unsigned char* suspect;   // [tpad] close-pair flags of the own targets (FLAGS kernels), else null
     long long tgt_base;      // global body index of own target 0 (multiple of NB_TILE)
     long long n_local;       // real (unpadded) own targets
     int tpad;                // padded own targets (multiple of the i-tile)

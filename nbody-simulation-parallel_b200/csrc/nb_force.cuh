@@ -29,16 +29,21 @@ template <> struct NbReal<true> { using type = double; };
 // FP32: one tile against TI targets.  npos holds the NEGATED target coordinates (the packed add
 // takes them as a broadcast scalar operand).  a[][] receives this tile's FP32 partial sums.
 //
-// EXACT = false (fast pass): no per-pair cut-off work at all -- FSETP/FSEL are ALU-pipe
-// instructions and on sm_100 every ALU instruction costs the FMA pipe two cycles (measured:
-// fma 72 % + alu 27 % = 99 % busy with the select in the loop).  Instead the pass tracks the
-// minimum r^2 it saw (one FMNMX3 per two pairs) and the caller REDOES the tile with
-// EXACT = true when that minimum is under the cut-off: the tile holding the thread's own
-// targets (self pair, r^2 = 0), exact duplicates, and genuinely close pairs.  NaN/inf produced
-// by rcp(0) in a fast pass are discarded with the rest of that pass.
-// EXACT = true: hard cut-off per pair (methods.cpp:119): pairs with r^2 < cutoff are DROPPED,
-// which also removes the self pair and exact duplicates: rcp(+inf) = 0.
-template <int D, int TI, int JS, bool EXACT>
+// The loop is register-file bound on sm_100 (one operand fetch per clock per SM sub-partition:
+// 25 fetches per packed chain without any cut-off work, 22 FMA-pipe clocks), so every extra
+// instruction in it costs its operand count.  Three flavours:
+// NB_EXACT   hard cut-off per pair (methods.cpp:119): pairs with r^2 < cutoff are DROPPED, which
+//            also removes the self pair and exact duplicates: rcp(+inf) = 0.  FSETP+FSEL per pair.
+// NB_TRACKED no per-pair cut-off work; tracks the minimum r^2 seen (one FMNMX3 per two pairs) and
+//            the caller REDOES the tile with NB_EXACT when that minimum is under the cut-off (the
+//            tile holding the thread's own targets, duplicates, genuinely close pairs).  NaN/inf
+//            produced by rcp(0) in such a pass are discarded with the rest of it.
+// NB_PLAIN   nothing at all; legal only where a pre-pass (nb_grid_*_kernel) proved that no target
+//            of the warp has another body within the cut-off radius and the tile does not hold
+//            the warp's own targets.
+enum { NB_PLAIN = 0, NB_TRACKED = 1, NB_EXACT = 2 };
+
+template <int D, int TI, int JS, int MODE>
 __device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, int part, float cutoff,
                                              const float (&npos)[TI][3], float2 (&a)[TI][3]) {
     const float4* sx = reinterpret_cast<const float4*>(stage);
@@ -74,10 +79,10 @@ __device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, in
                     dz = __fadd2_rn(zs, make_float2(npos[t][2], npos[t][2]));
                     r2 = __ffma2_rn(dz, dz, r2);
                 }
-                if (EXACT) {
+                if (MODE == NB_EXACT) {
                     r2.x = (r2.x >= cutoff) ? r2.x : inf;
                     r2.y = (r2.y >= cutoff) ? r2.y : inf;
-                } else {
+                } else if (MODE == NB_TRACKED) {
                     rmin = fminf(rmin, fminf(r2.x, r2.y));    // one FMNMX3
                 }
                 float2 inv;
@@ -95,7 +100,7 @@ __device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, in
 }
 
 // FP64: one tile against TI targets (pos holds the plain target coordinates).
-template <int D, int TI, int JS>
+template <int D, int TI, int JS, bool EXACT>
 __device__ __forceinline__ void nb_tile_f64(const double* __restrict__ stage, int part, double cutoff,
                                             const double (&pos)[TI][3], double (&accd)[TI][3]) {
     const double2* sx = reinterpret_cast<const double2*>(stage);
@@ -123,7 +128,7 @@ __device__ __forceinline__ void nb_tile_f64(const double* __restrict__ stage, in
                     r2 = fma(dz, dz, r2);
                 }
                 double inv = nb_rcp_f64(r2);
-                inv = (r2 >= cutoff) ? inv : 0.0;             // drop (also kills the NaN of r2 = 0)
+                if (EXACT) inv = (r2 >= cutoff) ? inv : 0.0;  // drop (also kills the NaN of r2 = 0)
                 const double s = ms * (inv * inv);
                 accd[t][0] = fma(s, dx, accd[t][0]);
                 accd[t][1] = fma(s, dy, accd[t][1]);
@@ -134,7 +139,9 @@ __device__ __forceinline__ void nb_tile_f64(const double* __restrict__ stage, in
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int D, bool F64, int TI, int JS, int BLOCK>
+// FLAGS = true: P.suspect[] (from the close-pair pre-pass) selects NB_PLAIN / NB_EXACT per warp and
+// tile; FLAGS = false: self-contained NB_TRACKED pass with redo (FP32) or NB_EXACT always (FP64).
+template <int D, bool F64, int TI, int JS, int BLOCK, bool FLAGS>
 __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) {
     using real = typename NbReal<F64>::type;
     constexpr int NP = D + 1;                       // planes per tile
@@ -221,13 +228,18 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
 
         // register-resident targets of this thread's group
         real tpos[TI][3];
+        int own_tile[TI];
+        bool suspect = false;
 #pragma unroll
         for (int t = 0; t < TI; ++t) {
             const long long b = P.tgt_base + (long long)it * ITILE + group + t * GROUPS;
+            own_tile[t] = (int)(b / NB_TILE);
             const real* tb = src + (size_t)(b / NB_TILE) * TILE_ELEMS + (b % NB_TILE);
 #pragma unroll
             for (int d = 0; d < 3; ++d) tpos[t][d] = (d < D) ? tb[d * NB_TILE] : real(0);
+            if constexpr (FLAGS) suspect |= P.suspect[it * ITILE + group + t * GROUPS] != 0;
         }
+        const bool warp_suspect = FLAGS ? (__any_sync(0xffffffffu, suspect) != 0) : false;
         double accd[TI][3];
 #pragma unroll
         for (int t = 0; t < TI; ++t)
@@ -256,14 +268,30 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
             const int slot = k % NB_STAGES;
             nb_mbar_wait(&full_bar[slot], (k / NB_STAGES) & 1u);
             const real* stage = ring + (size_t)slot * TILE_ELEMS;
+            // with FLAGS: exact pass for warps with a suspect target and for the tiles that hold the
+            // warp's own targets (self pairs); both conditions are warp-uniform
+            bool exact_tile = true;
+            if constexpr (FLAGS) {
+                exact_tile = warp_suspect;
+#pragma unroll
+                for (int tt = 0; tt < TI; ++tt) exact_tile |= (ts + t == own_tile[tt]);
+            }
             if constexpr (F64) {
-                nb_tile_f64<D, TI, JS>(reinterpret_cast<const double*>(stage), part, P.cutoff,
-                                       reinterpret_cast<const double(&)[TI][3]>(tpos), accd);
+                const double* dstage = reinterpret_cast<const double*>(stage);
+                if (exact_tile)
+                    nb_tile_f64<D, TI, JS, true>(dstage, part, P.cutoff, reinterpret_cast<const double(&)[TI][3]>(tpos), accd);
+                else
+                    nb_tile_f64<D, TI, JS, false>(dstage, part, P.cutoff, reinterpret_cast<const double(&)[TI][3]>(tpos), accd);
             } else {
                 const float* fstage = reinterpret_cast<const float*>(stage);
                 float2 a[TI][3];
-                const float rmin = nb_tile_f32<D, TI, JS, false>(fstage, part, cutoff_f, npos, a);
-                if (!(rmin >= cutoff_redo)) nb_tile_f32<D, TI, JS, true>(fstage, part, cutoff_f, npos, a);
+                if constexpr (FLAGS) {
+                    if (exact_tile) nb_tile_f32<D, TI, JS, NB_EXACT>(fstage, part, cutoff_f, npos, a);
+                    else nb_tile_f32<D, TI, JS, NB_PLAIN>(fstage, part, cutoff_f, npos, a);
+                } else {
+                    const float rmin = nb_tile_f32<D, TI, JS, NB_TRACKED>(fstage, part, cutoff_f, npos, a);
+                    if (!(rmin >= cutoff_redo)) nb_tile_f32<D, TI, JS, NB_EXACT>(fstage, part, cutoff_f, npos, a);
+                }
                 // per-tile flush of the short FP32 partial sums into FP64
 #pragma unroll
                 for (int tt = 0; tt < TI; ++tt)

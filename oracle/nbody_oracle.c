@@ -64,8 +64,8 @@ static inline int pair_force(int D, const double *pi, const double *pj, double m
     double dist_cb = dist_sq * dist;
     double force_mag = G * mi * mj / dist_cb;
     double mag = sqrt(dist_sq);
-    if (mag < 1e-10) { /* vector.h:95 -- unreachable after the cut-off when cutoff >= 1e-20 */
-        for (int d = 0; d < D; d++) force[d] = 0.0;
+    if (mag < 1e-10) { /* vector.h:95: normalized() returns the zero vector; unreachable when cutoff >= 1e-20 */
+        for (int d = 0; d < D; d++) force[d] = 0.0 * force_mag;   /* vector.h:39-43 (0 * inf = NaN for r = 0) */
         return 1;
     }
     for (int d = 0; d < D; d++) force[d] = (diff[d] / mag) * force_mag;

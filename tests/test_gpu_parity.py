@@ -95,6 +95,72 @@ def test_fp32_forces_vs_oracle_on_float_rounded_inputs(pkg, oracle, name):
     assert_fp32_parity(pkg, oracle, f, rb, name)
 
 
+# ------------------------------------------------------------------ close-pair pre-pass (hash grid)
+@pytest.mark.parametrize("prec", [64, 32])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_close_pair_prepass_matches_tracked_path(pkg, oracle, prec, dim):
+    """detect=1: a hash-grid pre-pass flags targets with a body inside the cut-off radius; flagged
+    warps and self tiles run the exact select pass, all others a pass with NO cut-off work.  Seed
+    the set with dropped pairs (r = 3e-6), kept close pairs (r = 2e-5, huge forces), duplicates."""
+    n = 7000
+    b = pkg.generators.uniform_cube(n, dim, seed=61)
+    rng = np.random.default_rng(5)
+    for k in range(0, 900, 2):
+        kind = (k // 2) % 3
+        off = np.zeros(dim)
+        if kind == 0:
+            off[rng.integers(dim)] = 3e-6            # r^2 = 9e-12 < 1e-10: dropped
+        elif kind == 1:
+            off[rng.integers(dim)] = 2e-5            # r^2 = 4e-10: kept, dominates both bodies
+        b[k + 1, :dim] = b[k, :dim] + off            # kind 2: exact duplicate
+    if prec == 32:
+        b = pkg.generators.round_to_float(b)
+    ref = oracle.forces(b)
+    got = {}
+    for detect in (1, 0):
+        for variant in (0, 4):
+            f = pkg.brute_force_cuda_n_body(b, prec, options={"detect": detect, "variant": variant})
+            assert np.all(np.isfinite(f))
+            if prec == 64:
+                e = rel(pkg, f, ref)
+                assert e.max() <= TOL64, f"detect={detect} variant={variant}: {e.max():.3e}"
+            else:
+                assert_fp32_parity(pkg, oracle, f, b, f"detect={detect} variant={variant}")
+            got[(detect, variant)] = f
+    assert rel(pkg, got[(1, 0)], got[(0, 0)]).max() <= (1e-13 if prec == 64 else 1e-6)
+    # and through the fused step: same trajectory with and without the pre-pass
+    a1 = pkg.brute_force_cuda_simulate(b, 1e-6, 5, prec, options={"detect": 1})
+    a0 = pkg.brute_force_cuda_simulate(b, 1e-6, 5, prec, options={"detect": 0})
+    assert np.abs(a1 - a0).max() <= 1e-9 * np.abs(a0).max()
+
+
+@pytest.mark.parametrize("name", ["degenerate3d_n9", "degenerate2d_n9", "tiny3d_n1", "ragged3d_n257", "c1_refrange3d_n1024"])
+@pytest.mark.parametrize("prec", [64, 32])
+def test_prepass_on_golden_edge_cases(pkg, oracle, name, prec):
+    g = load_golden(name)
+    b = g["bodies"] if prec == 64 else pkg.generators.round_to_float(g["bodies"])
+    f = pkg.brute_force_cuda_n_body(b, prec, options={"detect": 1})
+    if prec == 64:
+        if b.shape[0] > 1:
+            assert rel(pkg, f, g["forces_omp2"]).max() <= TOL64
+        else:
+            assert np.array_equal(f, np.zeros_like(f))
+    else:
+        assert_fp32_parity(pkg, oracle, f, b, name)
+
+
+def test_tiny_cutoff_is_clamped_to_the_normalized_guard(pkg, oracle):
+    """cutoff -> 0: Vector<D>::normalized() (vector.h:95) zeroes pairs with r < 1e-10 anyway, so the
+    ABI clamps the cut-off at 1e-20; exact duplicates then contribute 0 (the reference: 0 * inf)."""
+    b = pkg.generators.uniform_cube(3000, 3, seed=9)
+    b[11, :3] = b[10, :3]
+    ref = oracle.forces(b, cutoff=1e-20)
+    for detect in (0, 1):
+        f = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP64, cutoff=0.0, options={"detect": detect})
+        assert np.all(np.isfinite(f))
+        assert rel(pkg, f, ref).max() <= TOL64
+
+
 # ------------------------------------------------------------------ every kernel variant, ragged N
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
