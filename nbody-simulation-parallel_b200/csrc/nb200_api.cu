@@ -94,8 +94,13 @@ const Variant kVariants[] = {
     {4, 4, 256},   // 2:  256
     {2, 4, 128},   // 3:   64
     {2, 8, 128},   // 4:   32
+    // low-ILP, high-occupancy shapes: few chains per thread keep the three accumulate FFMA2 of a
+    // chain adjacent, so ptxas marks their shared multiplier .reuse (one operand fetch saved each)
+    {2, 1, 256},   // 5:  512, inner loop not unrolled
+    {1, 1, 256},   // 6:  256
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr int kNumAutoVariants = 5;     // the planner picks among 0..4; the rest are opt-in ("variant" option)
 
 typedef void (*ForceKernel)(const NbForceParams);
 
@@ -105,6 +110,8 @@ template <int D, bool F64, bool FLAGS> ForceKernel kernel_for(int v) {
         case 1: return nb_force_kernel<D, F64, 2, 1, 256, FLAGS>;
         case 2: return nb_force_kernel<D, F64, 4, 4, 256, FLAGS>;
         case 3: return nb_force_kernel<D, F64, 2, 4, 128, FLAGS>;
+        case 5: return nb_force_kernel<D, F64, 2, 1, 256, FLAGS, 1>;
+        case 6: return nb_force_kernel<D, F64, 1, 1, 256, FLAGS, 2>;
         default: return nb_force_kernel<D, F64, 2, 8, 128, FLAGS>;
     }
 }
@@ -363,8 +370,8 @@ int make_plan(nb200_ctx* ctx, const Shard& s, Plan* out) {
     if (v < 0 || v >= kNumVariants) {
         // largest i-tile that still gives every resident CTA >= 8 units at >= 8 tiles per unit,
         // else the smallest i-tile
-        v = kNumVariants - 1;
-        for (int c = 0; c < kNumVariants; ++c) {
+        v = kNumAutoVariants - 1;
+        for (int c = 0; c < kNumAutoVariants; ++c) {
             int g = 0;
             if (resident(c, &g) < 0) continue;
             const long long nit = (span + kVariants[c].itile() - 1) / kVariants[c].itile();

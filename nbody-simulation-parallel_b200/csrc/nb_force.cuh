@@ -43,7 +43,10 @@ template <> struct NbReal<true> { using type = double; };
 //            the warp's own targets.
 enum { NB_PLAIN = 0, NB_TRACKED = 1, NB_EXACT = 2 };
 
-template <int D, int TI, int JS, int MODE>
+#define NB_STR_(x) #x
+#define NB_UNROLL(n) _Pragma(NB_STR_(unroll n))
+
+template <int D, int TI, int JS, int MODE, int UNR>
 __device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, int part, float cutoff,
                                              const float (&npos)[TI][3], float2 (&a)[TI][3]) {
     const float4* sx = reinterpret_cast<const float4*>(stage);
@@ -57,7 +60,7 @@ __device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, in
 
     const float inf = __int_as_float(0x7f800000);
     float rmin = inf;
-#pragma unroll 2
+    NB_UNROLL(UNR)
     for (int q = part; q < NB_TILE / 4; q += JS) {
         const float4 X = sx[q], Y = sy[q], M = sm[q];
         float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -141,7 +144,7 @@ __device__ __forceinline__ void nb_tile_f64(const double* __restrict__ stage, in
 // ---------------------------------------------------------------------------------------------
 // FLAGS = true: P.suspect[] (from the close-pair pre-pass) selects NB_PLAIN / NB_EXACT per warp and
 // tile; FLAGS = false: self-contained NB_TRACKED pass with redo (FP32) or NB_EXACT always (FP64).
-template <int D, bool F64, int TI, int JS, int BLOCK, bool FLAGS>
+template <int D, bool F64, int TI, int JS, int BLOCK, bool FLAGS, int UNR = 2>
 __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) {
     using real = typename NbReal<F64>::type;
     constexpr int NP = D + 1;                       // planes per tile
@@ -286,11 +289,11 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
                 const float* fstage = reinterpret_cast<const float*>(stage);
                 float2 a[TI][3];
                 if constexpr (FLAGS) {
-                    if (exact_tile) nb_tile_f32<D, TI, JS, NB_EXACT>(fstage, part, cutoff_f, npos, a);
-                    else nb_tile_f32<D, TI, JS, NB_PLAIN>(fstage, part, cutoff_f, npos, a);
+                    if (exact_tile) nb_tile_f32<D, TI, JS, NB_EXACT, UNR>(fstage, part, cutoff_f, npos, a);
+                    else nb_tile_f32<D, TI, JS, NB_PLAIN, UNR>(fstage, part, cutoff_f, npos, a);
                 } else {
-                    const float rmin = nb_tile_f32<D, TI, JS, NB_TRACKED>(fstage, part, cutoff_f, npos, a);
-                    if (!(rmin >= cutoff_redo)) nb_tile_f32<D, TI, JS, NB_EXACT>(fstage, part, cutoff_f, npos, a);
+                    const float rmin = nb_tile_f32<D, TI, JS, NB_TRACKED, UNR>(fstage, part, cutoff_f, npos, a);
+                    if (!(rmin >= cutoff_redo)) nb_tile_f32<D, TI, JS, NB_EXACT, UNR>(fstage, part, cutoff_f, npos, a);
                 }
                 // per-tile flush of the short FP32 partial sums into FP64
 #pragma unroll

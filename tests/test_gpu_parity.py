@@ -163,7 +163,7 @@ def test_tiny_cutoff_is_clamped_to_the_normalized_guard(pkg, oracle):
 
 # ------------------------------------------------------------------ every kernel variant, ragged N
 @pytest.mark.parametrize("dim", [2, 3])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("seg_tiles", [1, 3, 0])
 def test_all_variants_and_segmentations(pkg, oracle, dim, variant, seg_tiles):
     n = 2500 + 37 * variant                      # never a multiple of the tile or the i-tile
