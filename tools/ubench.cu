@@ -12,7 +12,7 @@
 __device__ __forceinline__ float rcpf(float x) { float y; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
-enum { FFMA_S, FFMA2_REUSE, FFMA2_3DIST, FFMA2_SQ, FADD2_BC, FMUL2_SQ, MIX, MIX_NOCUT, DFMA_, DFMA_3DIST, MUFU_, FSEL_, MIX_MIN, MIX_RCP4 };
+enum { FFMA_S, FFMA2_REUSE, FFMA2_3DIST, FFMA2_SQ, FADD2_BC, FMUL2_SQ, MIX, MIX_NOCUT, DFMA_, DFMA_3DIST, MUFU_, FSEL_, MIX_MIN, MIX_RCP4, MIX_SACC, MIX_SACC1, MIX_SACC2 };
 
 template <int MODE> __global__ void __launch_bounds__(256) k(float* out, unsigned long long* stamp, float a, float b) {
     float2 acc[NACC], x[NACC], y[NACC];
@@ -42,7 +42,7 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, unsigne
             else if (MODE == DFMA_3DIST) dacc[i] = fma(dx[i], dy[i], dacc[i]);
             else if (MODE == MUFU_) acc[i].x = rcpf(acc[i].x);
             else if (MODE == FSEL_) { acc[i].x = acc[i].x >= a ? acc[i].x : b; acc[i].y = acc[i].y >= b ? acc[i].y : a; a += 1e-9f; }
-            else if (MODE == MIX || MODE == MIX_NOCUT || MODE == MIX_MIN || MODE == MIX_RCP4) {
+            else if (MODE == MIX || MODE == MIX_NOCUT || MODE == MIX_MIN || MODE == MIX_RCP4 || MODE == MIX_SACC || MODE == MIX_SACC1 || MODE == MIX_SACC2) {
                 // one packed pair-chain of the force kernel per i: 3 FADD2, FMUL2, 2 FFMA2, [2 FSETP+2 FSEL], 2 MUFU,
                 // 2 FMUL2, 3 FFMA2  (11 FMA-pipe packed ops)
                 const float2 s0 = make_float2(a + it, b + it);
@@ -53,11 +53,15 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, unsigne
                 float2 s;
                 if (MODE == MIX_RCP4) { const float2 r4 = __fmul2_rn(r2, r2); s = make_float2(rcpf(r4.x), rcpf(r4.y)); s = __fmul2_rn(s, b2); }
                 else { float2 inv = make_float2(rcpf(r2.x), rcpf(r2.y)); s = __fmul2_rn(inv, inv); s = __fmul2_rn(s, b2); }
-                acc[i] = __ffma2_rn(s, d0, acc[i]);
-                dacc[i] = dacc[i];   // keep signature
-                x[i] = x[i];
-                acc[(i + 1) % NACC] = __ffma2_rn(s, d1, acc[(i + 1) % NACC]);
-                acc[(i + 2) % NACC] = __ffma2_rn(s, d2, acc[(i + 2) % NACC]);
+                // accumulate: packed FFMA2 has three distinct 64-bit operands (register-fetch bound);
+                // MIX_SACC* replace 3/1/2 of them by two scalar FFMA each
+                constexpr int NS = MODE == MIX_SACC ? 3 : MODE == MIX_SACC2 ? 2 : MODE == MIX_SACC1 ? 1 : 0;
+                if (NS >= 1) { acc[i].x = fmaf(s.x, d0.x, acc[i].x); acc[i].y = fmaf(s.y, d0.y, acc[i].y); }
+                else acc[i] = __ffma2_rn(s, d0, acc[i]);
+                if (NS >= 2) { acc[(i + 1) % NACC].x = fmaf(s.x, d1.x, acc[(i + 1) % NACC].x); acc[(i + 1) % NACC].y = fmaf(s.y, d1.y, acc[(i + 1) % NACC].y); }
+                else acc[(i + 1) % NACC] = __ffma2_rn(s, d1, acc[(i + 1) % NACC]);
+                if (NS >= 3) { acc[(i + 2) % NACC].x = fmaf(s.x, d2.x, acc[(i + 2) % NACC].x); acc[(i + 2) % NACC].y = fmaf(s.y, d2.y, acc[(i + 2) % NACC].y); }
+                else acc[(i + 2) % NACC] = __ffma2_rn(s, d2, acc[(i + 2) % NACC]);
             }
         }
     }
@@ -105,6 +109,9 @@ int main() {
         run<MIX_NOCUT>("pair chain no cut-off", 22, c);
         run<MIX_MIN>("pair chain + FMNMX3 min", 22, c);
         run<MIX_RCP4>("pair chain rcp(r2*r2), no cut", 22, c);
+        run<MIX_SACC1>("pair chain, 1 of 3 acc scalar", 22, c);
+        run<MIX_SACC2>("pair chain, 2 of 3 acc scalar", 22, c);
+        run<MIX_SACC>("pair chain, all acc scalar FFMA", 22, c);
         run<DFMA_>("DFMA reuse", 1, c);
         run<DFMA_3DIST>("DFMA 3 distinct", 1, c);
         run<MUFU_>("MUFU.RCP", 1, c);
