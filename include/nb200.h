@@ -87,9 +87,11 @@ void nb200_destroy(nb200_ctx* ctx);
  * stride in bytes (40 for D=2, 56 for D=3, or larger).  Every rank passes ALL n bodies. */
 int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride);
 
-/* Writes position and velocity (mass untouched) of the bodies this context owns back into an
- * AoS array of ALL n bodies: every body for nb200_create contexts, rows [lo,hi) of
- * nb200_shard_range for nb200_create_rank contexts. */
+/* Writes position and velocity of the bodies this context owns back into an AoS array of ALL n
+ * bodies: every body for nb200_create contexts, rows [lo,hi) of nb200_shard_range for
+ * nb200_create_rank contexts.  Same stride as the upload.  With packed records (stride 40 / 56)
+ * whole rows are copied, i.e. the mass field is rewritten with the uploaded mass (a step never
+ * changes it); with padded records only position and velocity are written. */
 int nb200_download_aos(nb200_ctx* ctx, void* bodies, size_t stride);
 
 /* Owned target range [lo, hi) in body indices. */

@@ -107,7 +107,7 @@ class NBodyCuda:
         self._stride = b.strides[0] if self.n else 8 * (2 * self.dim + 1)
 
     def download(self, into: np.ndarray) -> np.ndarray:
-        """Overwrite position and velocity of the owned rows of ``into`` (masses untouched)."""
+        """Overwrite the owned rows of ``into`` with the advanced bodies (mass = the uploaded mass)."""
         if into.dtype != np.float64 or not into.flags.c_contiguous or into.shape != (self.n, 2 * self.dim + 1):
             raise ValueError("download target must be a C-contiguous float64 (n, 2D+1) array")
         self._check(self._lib.nb200_download_aos(self._h, into.ctypes.data, self._stride), "download")

@@ -144,6 +144,8 @@ struct Shard {
     void* src[2] = {nullptr, nullptr};
     double *acc = nullptr, *pos = nullptr, *vel = nullptr, *mass = nullptr, *forces = nullptr;
     double* aos_dev = nullptr;            // staging image of the AoS bodies (upload/download)
+    size_t aos_bytes = 0;
+    unsigned long long* bounds = nullptr; // [2] bit patterns of max |coordinate|, max |mass| of the image
     double* energy = nullptr;             // [2]
     unsigned *tile_done = nullptr, *sched = nullptr;
     ncclComm_t comm_nccl = nullptr;
@@ -255,6 +257,7 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
     CK(cudaMalloc(&s.mass, tp * sizeof(double)));
     CK(cudaMalloc(&s.forces, std::max<size_t>(1, (size_t)s.n_local * D) * sizeof(double)));
     CK(cudaMalloc(&s.energy, 2 * sizeof(double)));
+    CK(cudaMalloc(&s.bounds, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc(&s.tile_done, (tp / 32 + 1) * sizeof(unsigned)));
     CK(cudaMemset(s.tile_done, 0, (tp / 32 + 1) * sizeof(unsigned)));
     {
@@ -295,7 +298,7 @@ void free_shard(Shard& s) {
     cudaFree(s.grid_keys); cudaFree(s.grid_counts); cudaFree(s.suspect);
     for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
     cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
-    cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.tile_done); cudaFree(s.sched);
+    cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.bounds); cudaFree(s.tile_done); cudaFree(s.sched);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
     if (s.ev_pass_done) cudaEventDestroy(s.ev_pass_done);
@@ -910,26 +913,33 @@ int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
     // FP32 pair math runs on power-of-two-scaled sources (exact): |x'| <= 1, m' <= 1
     ctx->pos_scale = ctx->mass_scale = 1.0;
     ctx->xmax = 1.0;
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        const size_t bytes = std::max<size_t>(1, ctx->n) * stride;
+        if (s.aos_dev && s.aos_bytes < bytes) { CK(cudaFree(s.aos_dev)); s.aos_dev = nullptr; }
+        if (!s.aos_dev) { CK(cudaMalloc(&s.aos_dev, bytes)); s.aos_bytes = bytes; }
+        if (ctx->n) CK(cudaMemcpyAsync(s.aos_dev, bodies, ctx->n * stride, cudaMemcpyHostToDevice, s.compute));
+    }
     if (ctx->n) {
-        double xmax = 0.0, mmax = 0.0;
-        const double* p = static_cast<const double*>(bodies);
-        for (size_t i = 0; i < ctx->n; ++i) {
-            const double* r = p + i * sd;
-            for (int d = 0; d < D; ++d) xmax = std::max(xmax, fabs(r[d]));
-            mmax = std::max(mmax, fabs(r[2 * D]));
-        }
+        // bounds of the image, reduced on the device that already holds it (shard 0)
+        Shard& s = ctx->shards[0];
+        CK(cudaSetDevice(s.device));
+        CK(cudaMemsetAsync(s.bounds, 0, 2 * sizeof(unsigned long long), s.compute));
+        const int blocks = (int)std::min<long long>(4LL * s.sms, ((long long)ctx->n + 255) / 256);
+        if (D == 3) nb_bounds_kernel<3><<<blocks, 256, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, s.bounds);
+        else nb_bounds_kernel<2><<<blocks, 256, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, s.bounds);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        double hb[2] = {0.0, 0.0};
+        CK(cudaMemcpyAsync(hb, s.bounds, sizeof hb, cudaMemcpyDeviceToHost, s.compute));
+        CK(cudaStreamSynchronize(s.compute));
+        const double xmax = hb[0], mmax = hb[1];
         int ex = 0;
         if (xmax > 0 && isfinite(xmax)) ctx->xmax = xmax;
         if (!ctx->f64) {
             if (xmax > 0 && isfinite(xmax)) { frexp(xmax, &ex); ctx->pos_scale = ldexp(1.0, -ex); }
             if (mmax > 0 && isfinite(mmax)) { frexp(mmax, &ex); ctx->mass_scale = ldexp(1.0, -ex); }
         }
-    }
-    for (Shard& s : ctx->shards) {
-        CK(cudaSetDevice(s.device));
-        const size_t bytes = std::max<size_t>(1, ctx->n) * stride;
-        if (!s.aos_dev) CK(cudaMalloc(&s.aos_dev, bytes));
-        if (ctx->n) CK(cudaMemcpyAsync(s.aos_dev, bodies, ctx->n * stride, cudaMemcpyHostToDevice, s.compute));
     }
     int rc = pack_sources(ctx);
     if (rc) return rc;
@@ -959,9 +969,16 @@ int nb200_download_aos(nb200_ctx* ctx, void* bodies, size_t stride) {
         else nb_unpack_kernel<2><<<blocks, threads, 0, s.compute>>>(rows, sd, s.n_local, s.tpad, s.pos, s.vel);
         CK(cudaGetLastError());
         ctx->launches++;
-        // copy only position+velocity of each row so the caller's masses stay untouched
-        CK(cudaMemcpy2DAsync(static_cast<char*>(bodies) + (size_t)s.tgt_base * stride, stride, rows, stride,
-                             (size_t)2 * D * sizeof(double), (size_t)s.n_local, cudaMemcpyDeviceToHost, s.compute));
+        char* dst = static_cast<char*>(bodies) + (size_t)s.tgt_base * stride;
+        if (stride == (size_t)(2 * D + 1) * sizeof(double)) {
+            // packed Body<D> records: one contiguous copy of whole rows (the mass column of the image
+            // still holds the uploaded masses, so the caller gets back the bytes it passed in)
+            CK(cudaMemcpyAsync(dst, rows, (size_t)s.n_local * stride, cudaMemcpyDeviceToHost, s.compute));
+        } else {
+            // padded records: position+velocity only, the caller's padding stays untouched
+            CK(cudaMemcpy2DAsync(dst, stride, rows, stride, (size_t)2 * D * sizeof(double), (size_t)s.n_local,
+                                 cudaMemcpyDeviceToHost, s.compute));
+        }
     }
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));

@@ -41,6 +41,39 @@ __global__ void nb_pack_kernel(const double* __restrict__ aos, size_t stride_d, 
     }
 }
 
+// max |coordinate| and max |mass| over the AoS image (FP32 mode picks its power-of-two source
+// scales from them).  Non-negative doubles order like their bit patterns, so the reduction ends
+// in one 64-bit atomicMax per warp.  NaNs are ignored (every comparison with them is false).
+template <int D>
+__global__ void __launch_bounds__(256) nb_bounds_kernel(const double* __restrict__ aos, size_t stride_d,
+                                                         long long n, unsigned long long* __restrict__ out) {
+    double xm = 0.0, mm = 0.0;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < n;
+         b += (long long)gridDim.x * blockDim.x) {
+        const double* rec = aos + (size_t)b * stride_d;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const double v = fabs(rec[d]);
+            if (v > xm) xm = v;
+        }
+        const double m = fabs(rec[2 * D]);
+        if (m > mm) mm = m;
+    }
+    unsigned long long xb = (unsigned long long)__double_as_longlong(xm);
+    unsigned long long mb = (unsigned long long)__double_as_longlong(mm);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long x2 = __shfl_xor_sync(0xffffffffu, xb, o);
+        const unsigned long long m2 = __shfl_xor_sync(0xffffffffu, mb, o);
+        xb = x2 > xb ? x2 : xb;
+        mb = m2 > mb ? m2 : mb;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&out[0], xb);
+        atomicMax(&out[1], mb);
+    }
+}
+
 // master state of the own targets -> rows [tgt_base, tgt_base + n_local) of an AoS device image
 template <int D>
 __global__ void nb_unpack_kernel(double* __restrict__ aos_rows, size_t stride_d, long long n_local,
