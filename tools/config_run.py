@@ -32,7 +32,7 @@ CONFIGS = {
     "c2": (3, 16384, "cube", 100, 1e-4),
     "c3": (2, 65536, "jittered", 100, 1e-5),
     "c4": (3, 262144, "plummer", 100, 1e-3),
-    "c5": (3, 1 << 20, "cube", 10, 1e-4),
+    "c5": (3, 1 << 20, "cube", 10, 1e-6),
 }
 
 
