@@ -177,6 +177,21 @@ def run_reference_arm(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------- ncu evidence
+def ncu_traffic(n: int, prec: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the force kernel, per launch, from the committed
+    `ncu --set full` capture of this workload (profiles/*_summary.json, written by tools/ncu_summary.py)."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", f"*force_f{prec}_n{n}_*summary.json"))):
+        try:
+            k = json.load(open(f))["kernels"][0]
+            best = (int(k["dram_traffic_bytes"]), os.path.relpath(f, ROOT))
+        except Exception:
+            continue
+    return best if best else (None, None)
+
+
 # ------------------------------------------------------------------------------------- host buffers
 def shared_pinned_bodies(bodies, rank, world, torch, barrier):
     """The e2e leg's host array: page-locked; for world > 1 one /dev/shm mapping shared by all ranks."""
@@ -329,6 +344,8 @@ def run_product_arm(args) -> None:
     except Exception:
         pass
     sm_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+    measured_peak = pkg.measure_fp32_peak(local) * world if prec == 32 else None   # live, CUDA events, this GPU
+    traffic, traffic_src = ncu_traffic(n, prec) if world == 1 else (None, None)
     lanes = SM_LANES_FP32 if prec == 32 else 64
     peak_tflops = sms * lanes * 2 * sm_max * 1e6 / 1e12 * world
     achieved_tflops = value * 1e9 * FLOPS_PER_INTERACTION / 1e12
@@ -340,8 +357,11 @@ def run_product_arm(args) -> None:
                        "HBM and bf16-tensor peaks, neither bounds this kernel (20 flops/interaction convention)",
         "frac_at_observed_clock": (round(achieved_tflops / (peak_tflops * clocks["sm_mhz"] / sm_max), 4)
                                    if clocks.get("sm_mhz") else None),
+        "peak_measured": round(measured_peak, 2) if measured_peak else None,
+        "frac_of_measured": round(achieved_tflops / measured_peak, 4) if measured_peak else None,
+        "peak_measured_source": "nb200_measure_fp32_peak: independent packed FFMA2 chains timed with CUDA events in this run",
         "fma_pipe_lane_ops_per_interaction": 11,
-        "traffic": None,
+        "traffic": traffic, "traffic_source": traffic_src,
         "hbm_algorithmic_bytes_per_step": n * (16 if prec == 32 else 32) + n * (2 * DIM * 8 * 2 + 8 + 3 * 8 * 2),
     }
     line = {

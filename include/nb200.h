@@ -115,6 +115,11 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
  * pairs under the cut-off excluded).  Rank contexts return their shard's partial sums. */
 int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, double* potential);
 
+/* Measurement aid: the FP32 FMA-pipe throughput this device sustains on independent packed
+ * FFMA2 chains (TFLOP/s, 2 flops per lane-op), timed with CUDA events.  It is the denominator of
+ * the FP32 roofline fraction bench.py reports next to the nominal SMs x 128 x 2 x clock figure. */
+int nb200_measure_fp32_peak(int device, double* tflops);
+
 /* utils.h:170-219 on the host-resident arrays (n*D doubles each): percentage of bodies whose
  * every component is within 1 % of the reference (absolute 1e-9 test when |ref| < 1e-20). */
 int nb200_accuracy_pct(nb200_ctx* ctx, const double* forces, const double* reference, double* pct);

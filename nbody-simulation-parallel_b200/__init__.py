@@ -158,6 +158,17 @@ class NBodyCuda:
         return p.decode() if p else ""
 
 
+def measure_fp32_peak(device: int = 0) -> float:
+    """Measured FP32 FMA-pipe peak of ``device`` in TFLOP/s (nb200_measure_fp32_peak)."""
+    lib = _lib.load()
+    t = ctypes.c_double()
+    rc = lib.nb200_measure_fp32_peak(device, ctypes.byref(t))
+    if rc != 0:
+        msg = lib.nb200_last_error(None)
+        raise NB200Error(f"nb200_measure_fp32_peak failed ({rc}): {msg.decode() if msg else ''}")
+    return t.value
+
+
 def brute_force_cuda_n_body(bodies: np.ndarray, precision: int = NB200_FP64, ngpus: int = 1, G: float = G_REF,
                             cutoff: float = CUTOFF_REF, options: dict | None = None) -> np.ndarray:
     """Forces on every body, (n, D) float64 in body order -- the ``BruteForce_CUDA`` method beside
@@ -189,4 +200,4 @@ def brute_force_cuda_simulate(bodies: np.ndarray, dt: float, steps: int, precisi
 
 
 __all__ = ["NBodyCuda", "NB200Error", "NB200_FP32", "NB200_FP64", "G_REF", "CUTOFF_REF",
-           "brute_force_cuda_n_body", "brute_force_cuda_simulate", "generators"]
+           "measure_fp32_peak", "brute_force_cuda_n_body", "brute_force_cuda_simulate", "generators"]

@@ -1205,6 +1205,38 @@ int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, do
     return NB200_OK;
 }
 
+int nb200_measure_fp32_peak(int device, double* tflops) {
+    nb200_ctx* ctx = nullptr;
+    if (!tflops) return fail(nullptr, NB200_EINVAL, "null tflops");
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || device < 0 || device >= have)
+        return fail(nullptr, NB200_ECUDA, "device %d not visible (libnb200 has no CPU fallback)", device);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 8;
+    float* out = nullptr;
+    CK(cudaMalloc(&out, (size_t)grid * 256 * sizeof(float)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int reps = 10;
+    for (int w = 0; w < 3; ++w) nb_fma_peak_kernel<<<grid, 256>>>(out, 1.0001f);
+    CK(cudaEventRecord(e0));
+    for (int w = 0; w < reps; ++w) nb_fma_peak_kernel<<<grid, 256>>>(out, 1.0001f);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = (double)grid * 256.0 * NB_PEAK_ITERS * NB_PEAK_NACC * 2.0 /*lanes*/ * 2.0 /*mul+add*/ * reps;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return NB200_OK;
+}
+
 int nb200_accuracy_pct(nb200_ctx* ctx, const double* forces, const double* reference, double* pct) {
     if (!ctx || !pct || (ctx->n && (!forces || !reference))) return NB200_EINVAL;
     const int D = ctx->dim;

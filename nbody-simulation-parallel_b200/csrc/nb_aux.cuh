@@ -232,3 +232,28 @@ __global__ void nb_grid_query_kernel(const real* __restrict__ src, long long tgt
             }
     suspect[li] = total > 1u;                             // anything besides the body itself
 }
+
+// ---------------------------------------------------------------------------------------------
+// Measured FP32 FMA-pipe peak of the device the roofline is quoted against (MEASURED_PEAKS.json
+// holds only HBM and bf16-tensor peaks): independent packed FFMA2 chains acc = x*x + acc, eight per
+// thread, two operands each so the register file is not the limit (tools/ubench.cu: 97 % of
+// SMs x 128 lanes x 2 x clock).
+#define NB_PEAK_ITERS 4096
+#define NB_PEAK_NACC 8
+__global__ void __launch_bounds__(256) nb_fma_peak_kernel(float* __restrict__ out, float a) {
+    float2 acc[NB_PEAK_NACC], x[NB_PEAK_NACC];
+#pragma unroll
+    for (int i = 0; i < NB_PEAK_NACC; ++i) {
+        acc[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
+        x[i] = make_float2(a + i * 1e-6f, a - i * 1e-6f);
+    }
+#pragma unroll 1
+    for (int it = 0; it < NB_PEAK_ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < NB_PEAK_NACC; ++i) acc[i] = __ffma2_rn(x[i], x[i], acc[i]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NB_PEAK_NACC; ++i) s += acc[i].x + acc[i].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}

@@ -362,3 +362,59 @@ def test_one_process_per_gpu_torchrun(exchange, overlap):
                         os.path.join(root, "tools", "mp_check.py"), "--exchange", exchange, "--overlap", str(overlap)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MP_CHECK" in r.stdout and " OK " in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+# ------------------------------------------------------------------ host-buffer path (upload / download)
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("prec", [64, 32])
+def test_padded_and_packed_records_round_trip(pkg, oracle, dim, prec):
+    """Body<D> records with a larger stride (padding the caller owns) and the packed 40/56-byte
+    records go through different download copies; both must return the stepped bodies, leave the
+    padding alone and hand the uploaded masses back."""
+    import ctypes
+    n = 3000
+    b = pkg.generators.uniform_cube(n, dim, seed=21)
+    want = oracle.simulate(pkg.generators.round_to_float(b) if prec == 32 else b, 1e-4, 3)
+    w = 2 * dim + 1
+    padded = np.full((n, w + 2), -7.0)
+    padded[:, :w] = b
+    lib = pkg._lib.load()
+    with pkg.NBodyCuda(dim, n, prec) as ctx:
+        h = ctx._h
+        assert lib.nb200_upload_aos(h, padded.ctypes.data, padded.strides[0]) == 0
+        ctx.step(1e-4, 3)
+        out = np.full((n, w + 2), 5.0)
+        out[:, 2 * dim] = b[:, 2 * dim]
+        assert lib.nb200_download_aos(h, out.ctypes.data, out.strides[0]) == 0
+        assert np.all(out[:, w:] == 5.0)                       # caller's padding untouched
+        assert np.array_equal(out[:, 2 * dim], b[:, 2 * dim])  # padded records: mass not written
+        assert lib.nb200_download_aos(h, out.ctypes.data, 8 * w) != 0   # stride must match the upload
+        ctx.upload(b)
+        ctx.step(1e-4, 3)
+        packed = np.zeros((n, w))
+        ctx.download(packed)
+        assert np.array_equal(packed[:, 2 * dim], b[:, 2 * dim])   # packed records: uploaded mass comes back
+    tol = 1e-12 if prec == 64 else 2e-6
+    scale = np.abs(want[:, :2 * dim]).max()
+    assert np.abs(out[:, :2 * dim] - want[:, :2 * dim]).max() <= tol * scale
+    assert np.array_equal(out[:, :2 * dim], packed[:, :2 * dim])
+
+
+def test_fp32_scales_come_from_the_device_side_bounds(pkg, oracle):
+    """The power-of-two source scales are reduced on the device from the uploaded image: huge and
+    tiny coordinate/mass ranges must both stay inside the FP32 parity band."""
+    for pos_mul, mass_mul in ((1.0e7, 1.0e8), (1.0e-6, 1.0e-9)):
+        b = pkg.generators.uniform_cube(2048, 3, seed=5)
+        b[:, :3] *= pos_mul
+        b[:, 6] *= mass_mul
+        b = pkg.generators.round_to_float(b)
+        cut = 1e-10 * pos_mul * pos_mul
+        f = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32, cutoff=cut)
+        ref = oracle.forces(b, cutoff=cut)
+        err = pkg.generators.relative_norm_error(f, ref)
+        assert np.percentile(err, 99) <= 1e-5 and err.max() <= 1e-4, (pos_mul, err.max())
+
+
+def test_measured_fp32_peak_is_plausible(pkg):
+    t = pkg.measure_fp32_peak(0)
+    assert 40.0 <= t <= 80.0, t      # B200: 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4 nominal

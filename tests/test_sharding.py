@@ -68,3 +68,14 @@ def test_world_size_2_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "GLOO_OK" in r.stdout
+
+
+def test_stratified_generator_keeps_bodies_apart(pkg):
+    for dim, n in ((2, 4096), (3, 1000), (2, 1000)):
+        b = pkg.generators.jittered_cube(n, dim, seed=3)
+        assert b.shape == (n, 2 * dim + 1) and b[:, :dim].min() >= 0.0 and b[:, :dim].max() <= 1.0
+        k = int(np.ceil(n ** (1.0 / dim) - 1e-9))
+        d = b[:, None, :dim] - b[None, :512, :dim]
+        r = np.sqrt((d * d).sum(-1))
+        r[r == 0] = np.inf
+        assert r.min() >= 0.5 / k - 1e-12
