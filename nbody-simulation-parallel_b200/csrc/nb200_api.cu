@@ -30,6 +30,7 @@
 #include "../../include/nb200.h"
 #include "nb_aux.cuh"
 #include "nb_force.cuh"
+#include "nb_force_sym.cuh"
 
 #define NB200_VERSION_STR "nb200 0.1 (sm_100a)"
 
@@ -155,6 +156,10 @@ struct Shard {
     unsigned* grid_counts = nullptr;
     unsigned grid_cap = 0;
     unsigned char* suspect = nullptr;                 // [tpad]
+    // pair-symmetric pass: first flat unit index of every own i-tile (device copy + the host image it mirrors)
+    int* unit_prefix = nullptr;
+    std::vector<int> unit_prefix_host;
+    int sym_seg_tiles = 0;
     // fused NVLink exchange (peer stores from the epilogue + flag handshake)
     unsigned long long* flags = nullptr;              // [2*kMaxWorldP2P]: step flags, then epoch flags, by writer rank
     int n_peers = 0;
@@ -190,7 +195,7 @@ struct nb200_ctx {
     unsigned long long epoch = 0;        // uploads so far (published on the epoch flags)
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
@@ -268,6 +273,7 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
         CK(cudaMalloc(&s.grid_counts, (size_t)cap * sizeof(unsigned)));
         CK(cudaMalloc(&s.suspect, tp));
         CK(cudaMemset(s.suspect, 1, tp));
+        CK(cudaMalloc(&s.unit_prefix, (tp / NB_SYM_ITILE + 2) * sizeof(int)));
     }
     CK(cudaMalloc(&s.flags, 2 * kMaxWorldP2P * sizeof(unsigned long long)));
     CK(cudaMemset(s.flags, 0, 2 * kMaxWorldP2P * sizeof(unsigned long long)));
@@ -279,6 +285,9 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
             CK(cudaFuncSetAttribute((const void*)pick_kernel(D, ctx->f64, v, fl != 0),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem_bytes(D, ctx->f64)));
+    if (!ctx->f64)
+        CK(cudaFuncSetAttribute((const void*)(D == 3 ? nb_force_sym_kernel<3> : nb_force_sym_kernel<2>),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nb_sym_smem_bytes(D)));
     return NB200_OK;
 }
 
@@ -295,7 +304,7 @@ void free_shard(Shard& s) {
         }
     }
     cudaFree(s.flags);
-    cudaFree(s.grid_keys); cudaFree(s.grid_counts); cudaFree(s.suspect);
+    cudaFree(s.grid_keys); cudaFree(s.grid_counts); cudaFree(s.suspect); cudaFree(s.unit_prefix);
     for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
     cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
     cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.bounds); cudaFree(s.tile_done); cudaFree(s.sched);
@@ -471,8 +480,9 @@ __global__ void nb_publish_epoch_kernel(NbForceParams P, int stride, unsigned lo
     }
 }
 
-int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsigned units_per_itile,
-                int mode, double G, double cutoff, double dt, int cur, const Handshake& hs = Handshake()) {
+// everything of NbForceParams that does not depend on the unit decomposition of one launch
+NbForceParams base_params(const nb200_ctx* ctx, const Shard& s, int mode, double G, double cutoff, double dt, int cur,
+                          const Handshake& hs) {
     NbForceParams P;
     memset(&P, 0, sizeof P);
     P.src = s.src[cur];
@@ -484,21 +494,9 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
     P.vel = s.vel;
     P.mass = s.mass;
     P.forces = s.forces;
-    P.suspect = pl.flags ? s.suspect : nullptr;
     P.tgt_base = s.tgt_base;
     P.n_local = s.n_local;
     P.tpad = s.tpad;
-    P.n_itiles = pl.n_itiles;
-    P.seg_tiles = pl.seg_tiles;
-    int nseg_total = 0;
-    for (int r = 0; r < 3; ++r) {
-        P.rng_begin[r] = rg.b[r];
-        P.rng_end[r] = rg.e[r];
-        P.rng_nseg[r] = nsegs(rg.b[r], rg.e[r], pl.seg_tiles);
-        nseg_total += P.rng_nseg[r];
-    }
-    P.lazy_wait = hs.lazy ? 1 : 0;
-    P.units_per_itile = units_per_itile;
     P.mode = mode;
     P.G = G;
     // FP32 sources are scaled by powers of two: x' = x ps, m' = m ms  =>  r'^2 = r^2 ps^2,
@@ -521,6 +519,24 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
             P.peer_rank[p] = s.peer_rank[p];
         }
     }
+    return P;
+}
+
+int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsigned units_per_itile,
+                int mode, double G, double cutoff, double dt, int cur, const Handshake& hs = Handshake()) {
+    NbForceParams P = base_params(ctx, s, mode, G, cutoff, dt, cur, hs);
+    P.suspect = pl.flags ? s.suspect : nullptr;
+    P.n_itiles = pl.n_itiles;
+    P.seg_tiles = pl.seg_tiles;
+    int nseg_total = 0;
+    for (int r = 0; r < 3; ++r) {
+        P.rng_begin[r] = rg.b[r];
+        P.rng_end[r] = rg.e[r];
+        P.rng_nseg[r] = nsegs(rg.b[r], rg.e[r], pl.seg_tiles);
+        nseg_total += P.rng_nseg[r];
+    }
+    P.lazy_wait = hs.lazy ? 1 : 0;
+    P.units_per_itile = units_per_itile;
     if (nseg_total == 0) return NB200_OK;
     const Variant& V = kVariants[pl.variant];
     ForceKernel k = pick_kernel(ctx->dim, ctx->f64, pl.variant, pl.flags);
@@ -529,6 +545,67 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
     k<<<grid, V.block, smem_bytes(ctx->dim, ctx->f64), s.compute>>>(P);
     CK(cudaGetLastError());
     ctx->launches++;
+    return NB200_OK;
+}
+
+// ---- pair-symmetric pass (FP32, one shard owning all sources): see nb_force_sym.cuh
+bool use_symmetric(const nb200_ctx* ctx) {
+    if (ctx->f64 || ctx->world != 1 || !use_detect(ctx)) return false;
+    return ctx->opt_symmetric != 0;
+}
+
+// symmetric force kernel over the own x own block, then the finish kernel (forces or integrate)
+int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff, double dt, int cur) {
+    const int D = ctx->dim;
+    const int tiles_per_itile = NB_SYM_ITILE / NB_TILE;
+    const int own_begin = (int)s.tile_lo, own_end = (int)s.tile_hi;
+    const int n_itiles = (own_end - own_begin + tiles_per_itile - 1) / tiles_per_itile;
+    int seg = ctx->opt_seg_tiles;
+    if (seg <= 0) seg = (own_end - own_begin) <= 1024 ? 8 : (own_end - own_begin) <= 2048 ? 16 : 32;
+    if ((int)s.unit_prefix_host.size() != n_itiles + 1 || s.sym_seg_tiles != seg) {
+        s.unit_prefix_host.assign(n_itiles + 1, 0);
+        for (int it = 0; it < n_itiles; ++it) {
+            const int above = own_end - std::min(own_end, own_begin + (it + 1) * tiles_per_itile);
+            s.unit_prefix_host[it + 1] = s.unit_prefix_host[it] + 1 + (above + seg - 1) / seg;
+        }
+        s.sym_seg_tiles = seg;
+        CK(cudaMemcpyAsync(s.unit_prefix, s.unit_prefix_host.data(), (n_itiles + 1) * sizeof(int),
+                           cudaMemcpyHostToDevice, s.compute));
+    }
+    NbSymParams Q;
+    memset(&Q, 0, sizeof Q);
+    Q.src = static_cast<const float*>(s.src[cur]);
+    Q.acc = s.acc;
+    Q.sched = s.sched;
+    Q.unit_prefix = s.unit_prefix;
+    Q.suspect = s.suspect;
+    Q.tgt_base = s.tgt_base;
+    Q.tpad = s.tpad;
+    Q.n_itiles = n_itiles;
+    Q.seg_tiles = seg;
+    Q.own_tile_begin = own_begin;
+    Q.own_tile_end = own_end;
+    Q.total_units = s.unit_prefix_host[n_itiles];
+    Q.cutoff = (float)(cutoff * ctx->pos_scale * ctx->pos_scale);
+    const void* kfn = D == 3 ? (const void*)nb_force_sym_kernel<3> : (const void*)nb_force_sym_kernel<2>;
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, NB_SYM_BLOCK, nb_sym_smem_bytes(D)));
+    const int grid = std::min(std::max(1, nb) * s.sms, Q.total_units);
+    if (D == 3) nb_force_sym_kernel<3><<<grid, NB_SYM_BLOCK, nb_sym_smem_bytes(D), s.compute>>>(Q);
+    else nb_force_sym_kernel<2><<<grid, NB_SYM_BLOCK, nb_sym_smem_bytes(D), s.compute>>>(Q);
+    CK(cudaGetLastError());
+    NbForceParams P = base_params(ctx, s, mode, G, cutoff, dt, cur, Handshake());
+    const int fb = (s.tpad + 255) / 256;
+    if (D == 3) nb_finish_kernel<3, float><<<fb, 256, 0, s.compute>>>(P);
+    else nb_finish_kernel<2, float><<<fb, 256, 0, s.compute>>>(P);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "%s: fp32 dim=%d n=%zu shards=1 pair-symmetric(TI=4,block=256,itile=1024) seg_tiles=%d i-tiles=%d "
+             "units=%d grid=%d tiles=%lld cutoff=grid-prepass(plain|exact) + finish kernel",
+             mode ? "step" : "forces", D, ctx->n, seg, n_itiles, Q.total_units, grid, ctx->ntiles);
+    ctx->plan = buf;
     return NB200_OK;
 }
 
@@ -891,6 +968,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "overlap")) ctx->opt_overlap = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "trace")) ctx->opt_trace = value != 0;
     else if (!strcmp(key, "detect")) ctx->opt_detect = value < 0 ? -1 : (value != 0);
+    else if (!strcmp(key, "symmetric")) ctx->opt_symmetric = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "exchange")) {
         if (value == 1 && !ctx->p2p_ready) return fail(ctx, NB200_ESTATE, "peer-store exchange is not attached");
         if (value == 0 && ctx->rank_mode && ctx->world > 1 && !ctx->detached && !ctx->shards[0].comm_nccl)
@@ -1007,8 +1085,12 @@ int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out)
         CK(cudaStreamWaitEvent(s.compute, s.ev_gather[ctx->cur], 0));
         CK(cudaEventRecord(s.ev_start, s.compute));
         if (pl.flags) { if (int rcd = launch_detect(ctx, s, cutoff_r2, ctx->cur)) return rcd; }
-        Ranges all(0, (int)ctx->ntiles);
-        rc = launch_pass(ctx, s, pl, all, (unsigned)total_units_per_itile(ctx, s, pl, false), 0, G, cutoff_r2, 0.0, ctx->cur);
+        if (use_symmetric(ctx)) {
+            rc = launch_symmetric(ctx, s, 0, G, cutoff_r2, 0.0, ctx->cur);
+        } else {
+            Ranges all(0, (int)ctx->ntiles);
+            rc = launch_pass(ctx, s, pl, all, (unsigned)total_units_per_itile(ctx, s, pl, false), 0, G, cutoff_r2, 0.0, ctx->cur);
+        }
         if (rc) return rc;
         CK(cudaEventRecord(s.ev_stop, s.compute));
         if (s.n_local > 0)
@@ -1108,6 +1190,8 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
                 Handshake hs = hs_remote;
                 hs.lazy = true;
                 rc = launch_pass(ctx, s, pl, own_first, upi, 1, G, cutoff_r2, dt, cur, hs);
+            } else if (use_symmetric(ctx)) {
+                rc = launch_symmetric(ctx, s, 1, G, cutoff_r2, dt, cur);
             } else {
                 if (use_nccl) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
                 Ranges all(0, NT);

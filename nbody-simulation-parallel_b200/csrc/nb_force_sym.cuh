@@ -1,0 +1,364 @@
+// nb_force_sym.cuh -- the pair-symmetric flavour of the force pass (FP32).
+//
+// The reference's sequential variant walks only j > i and scatters +-force to both bodies
+// (brute_force_seq_n_body, methods.cpp:18-39: forces[j] += f; forces[i] -= f).  This kernel does
+// the same on the GPU for the block of pairs whose two bodies BOTH belong to this shard: every
+// unordered pair is evaluated once and feeds two accumulators, so the shared part of the chain
+// (3 FADD2 + FMUL2 + 2 FFMA2 for d and r^2, MUFU.RCP, FMUL2 for 1/r^4) is paid once per two
+// interactions: 15 packed FMA-pipe instructions per two pairs of bodies = 7.5 lane-ops per
+// ordered interaction instead of 11.
+//
+// Work units: (i-tile of 1024 own targets) x (segment of source tiles strictly ABOVE the
+// i-tile), plus one diagonal unit per i-tile (its own four source tiles, evaluated as ordered
+// pairs by the ordinary tile functions).  A thread keeps four targets in registers ("a" side,
+// summed per tile into FP64 exactly like nb_force_kernel); the reaction on the streamed sources
+// ("b" side) is produced per lane for four sources at a time and reduced
+//   lane partials -> warp  : through a 32x12 shared-memory transpose (3 STS.128, 16 LDS, 16 FADD)
+//   warp sums     -> CTA   : per-warp [D][256] tile buffers, summed by the CTA after the tile
+//   CTA tile sums -> global: one FP64 atomicAdd per (source, component) per tile
+// The integrator/forces epilogue cannot be fused here (an i-tile also receives "b" sums from the
+// units of every lower i-tile), so nb_finish_kernel runs after the pass.
+#pragma once
+#include "nb_force.cuh"
+
+#define NB_SYM_TI 4
+#define NB_SYM_BLOCK 256
+#define NB_SYM_ITILE (NB_SYM_TI * NB_SYM_BLOCK)     // 1024 targets = 4 source tiles
+#define NB_SYM_ROW 14                               // floats per lane row of the transpose scratch (12 used):
+                                                    // 14 makes the STS.64 writes and the column reads bank-conflict free
+
+struct NbSymParams {
+    const float* src;            // tile-planar sources (current step)
+    double* acc;                 // [3][tpad] FP64 accumulators of the own targets
+    unsigned* sched;             // [2] unit counter + exit counter (self-resetting)
+    const int* unit_prefix;      // [n_itiles + 1] first flat unit index of every i-tile
+    const unsigned char* suspect;
+    long long tgt_base;          // first own body (multiple of NB_SYM_ITILE)
+    int tpad;
+    int n_itiles;                // own i-tiles
+    int seg_tiles;               // source tiles per symmetric unit
+    int own_tile_begin;          // tgt_base / NB_TILE
+    int own_tile_end;            // one past the last own source tile
+    int total_units;
+    float cutoff;                // scaled r^2 cut-off
+};
+
+static inline size_t nb_sym_smem_bytes(int dim) {
+    const size_t ring = (size_t)NB_STAGES * NB_TILE * (dim + 1) * sizeof(float);
+    const size_t bars = 2 * NB_STAGES * sizeof(uint64_t) + 16;
+    const size_t scr = (size_t)(NB_SYM_BLOCK / 32) * 2 * 32 * NB_SYM_ROW * sizeof(float);
+    const size_t bout = (size_t)2 * (NB_SYM_BLOCK / 32) * dim * NB_TILE * sizeof(float);
+    return ring + bars + scr + bout;
+}
+
+// One source tile against this thread's four targets, both directions.
+//   a[t][d]  += sum_j (m_j / r^4) d_ij          (this tile's FP32 partial of the target sums)
+//   wout[d][j] = sum over the warp's 128 targets of (m_i / r^4) d_ij   (NOT yet negated)
+// scr = this warp's two 32 x NB_SYM_ROW transpose buffers; lane = tid & 31.
+template <int D, int MODE>
+__device__ __forceinline__ void nb_tile_f32_sym(const float* __restrict__ stage, float cutoff,
+                                                const float (&npos)[NB_SYM_TI][3],
+                                                const float (&mi)[NB_SYM_TI],
+                                                float2 (&a)[NB_SYM_TI][3], float* __restrict__ scr,
+                                                float* __restrict__ wout, int lane) {
+    const float4* sx = reinterpret_cast<const float4*>(stage);
+    const float4* sy = sx + NB_TILE / 4;
+    const float4* sz = sy + NB_TILE / 4;                      // D == 3 only
+    const float4* sm = sx + D * (NB_TILE / 4);
+#pragma unroll
+    for (int t = 0; t < NB_SYM_TI; ++t)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a[t][d] = make_float2(0.f, 0.f);
+    const float inf = __int_as_float(0x7f800000);
+
+    // column-sum role of this lane in the transpose: output o = component * 4 + source (the word
+    // index inside a lane row), half hh = even / odd lane rows.  Word (2k + hh) * 14 + o lies in bank
+    // (28 k + 14 hh + o) mod 32: the 24 reducer lanes hit 24 distinct banks for every k.
+    const int o = lane >> 1, hh = lane & 1;
+    const bool reducer = lane < 8 * D;
+    const int oc = reducer ? o : 0;
+    const float* rbase = scr + hh * NB_SYM_ROW + oc;
+    float* wbase = wout + (oc >> 2) * NB_TILE + (oc & 3);
+    const bool writer = reducer && hh == 0;
+    auto reduce_store = [&](int q_done, int buf) {
+        const float* rb = rbase + buf * (32 * NB_SYM_ROW);
+        float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            v0 += rb[(2 * k) * NB_SYM_ROW];
+            v1 += rb[(2 * k + 2) * NB_SYM_ROW];
+        }
+        float v = v0 + v1;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (writer && q_done >= 0) wbase[q_done * 4] = v;
+    };
+
+#pragma unroll 1
+    for (int q = 0; q < NB_TILE / 4; ++q) {
+        const float4 X = sx[q], Y = sy[q], M = sm[q];
+        float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (D == 3) Z = sz[q];
+        float2 b[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 xs = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
+            const float2 ys = h ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
+            const float2 zs = h ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
+            const float2 ms = h ? make_float2(M.z, M.w) : make_float2(M.x, M.y);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) b[h][d] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < NB_SYM_TI; ++t) {
+                const float2 dx = __fadd2_rn(xs, make_float2(npos[t][0], npos[t][0]));
+                const float2 dy = __fadd2_rn(ys, make_float2(npos[t][1], npos[t][1]));
+                float2 r2 = __fmul2_rn(dx, dx);
+                r2 = __ffma2_rn(dy, dy, r2);
+                float2 dz;
+                if (D == 3) {
+                    dz = __fadd2_rn(zs, make_float2(npos[t][2], npos[t][2]));
+                    r2 = __ffma2_rn(dz, dz, r2);
+                }
+                if (MODE == NB_EXACT) {
+                    r2.x = (r2.x >= cutoff) ? r2.x : inf;
+                    r2.y = (r2.y >= cutoff) ? r2.y : inf;
+                }
+                float2 inv;
+                inv.x = nb_rcp_f32(r2.x);
+                inv.y = nb_rcp_f32(r2.y);
+                const float2 w = __fmul2_rn(inv, inv);
+                const float2 s = __fmul2_rn(w, ms);
+                const float2 u = __fmul2_rn(w, make_float2(mi[t], mi[t]));
+                a[t][0] = __ffma2_rn(s, dx, a[t][0]);
+                b[h][0] = __ffma2_rn(u, dx, b[h][0]);
+                a[t][1] = __ffma2_rn(s, dy, a[t][1]);
+                b[h][1] = __ffma2_rn(u, dy, b[h][1]);
+                if (D == 3) {
+                    a[t][2] = __ffma2_rn(s, dz, a[t][2]);
+                    b[h][2] = __ffma2_rn(u, dz, b[h][2]);
+                }
+            }
+        }
+        // the previous iteration's rows are complete (syncwarp at its end): reduce them while
+        // this iteration's chains are in flight, then publish this iteration's rows
+        reduce_store(q - 1, (q + 1) & 1);   // q = 0: nothing stored
+        float2* row = reinterpret_cast<float2*>(scr + (q & 1) * (32 * NB_SYM_ROW) + lane * NB_SYM_ROW);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            row[2 * d] = b[0][d];
+            row[2 * d + 1] = b[1][d];
+        }
+        __syncwarp();
+    }
+    reduce_store(NB_TILE / 4 - 1, (NB_TILE / 4 - 1) & 1);
+    __syncwarp();
+}
+
+template <int D>
+__global__ void __launch_bounds__(NB_SYM_BLOCK, 2) nb_force_sym_kernel(const NbSymParams P) {
+    constexpr int NP = D + 1;
+    constexpr int TI = NB_SYM_TI;
+    constexpr int BLOCK = NB_SYM_BLOCK;
+    constexpr int ITILE = NB_SYM_ITILE;
+    constexpr int TILE_ELEMS = NB_TILE * NP;
+    constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(float);
+    constexpr int NWARPS = BLOCK / 32;
+
+    extern __shared__ __align__(128) unsigned char nb_smem[];
+    float* ring = reinterpret_cast<float*>(nb_smem);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(nb_smem + (size_t)NB_STAGES * TILE_BYTES);
+    uint64_t* empty_bar = full_bar + NB_STAGES;
+    int* s_unit = reinterpret_cast<int*>(empty_bar + NB_STAGES);   // [0] i-tile (or -1), [1] segment
+    float* scr_all = reinterpret_cast<float*>(s_unit + 4);
+    float* bout_all = scr_all + (size_t)NWARPS * 2 * 32 * NB_SYM_ROW;   // [2][NWARPS][D][NB_TILE]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const float* __restrict__ src = P.src;
+    float* scr = scr_all + (size_t)warp * 2 * 32 * NB_SYM_ROW;
+
+    if (tid == 0) {
+        for (int s = 0; s < NB_STAGES; ++s) {
+            nb_mbar_init(&full_bar[s], 1);
+            nb_mbar_init(&empty_bar[s], NWARPS);
+        }
+        nb_fence_mbar_init();
+    }
+    __syncthreads();
+
+    unsigned kt = 0;          // tiles consumed by this CTA so far (ring position)
+    int bbuf = 0;             // which half of bout the next symmetric tile writes
+
+    for (;;) {
+        if (tid == 0) {
+            const int u = (int)atomicAdd(&P.sched[0], 1u);
+            int it = -1, sg = 0;
+            if (u < P.total_units) {
+                int lo = 0, hi = P.n_itiles;            // largest it with unit_prefix[it] <= u
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (P.unit_prefix[mid] <= u) lo = mid; else hi = mid;
+                }
+                it = lo;
+                sg = u - P.unit_prefix[lo];
+            }
+            s_unit[0] = it;
+            s_unit[1] = sg;
+        }
+        __syncthreads();
+        const int it = s_unit[0];
+        const int sg = s_unit[1];
+        __syncthreads();
+        if (it < 0) break;
+        // segment 0 = the diagonal unit (own four tiles, ordered pairs); segment s >= 1 = symmetric
+        const bool sym = sg > 0;
+        const int diag0 = P.own_tile_begin + it * (ITILE / NB_TILE);
+        const int ts = sym ? diag0 + ITILE / NB_TILE + (sg - 1) * P.seg_tiles : diag0;
+        const int te = sym ? min(ts + P.seg_tiles, P.own_tile_end) : min(diag0 + ITILE / NB_TILE, P.own_tile_end);
+        const int ntl = te - ts;
+
+        if (tid == 0) {
+            const int pre = min(NB_STAGES - 1, ntl);
+            for (int t = 0; t < pre; ++t) {
+                const unsigned k = kt + t;
+                const int slot = k % NB_STAGES;
+                nb_mbar_wait(&empty_bar[slot], ((k / NB_STAGES) & 1u) ^ 1u);
+                nb_mbar_expect_tx(&full_bar[slot], TILE_BYTES);
+                nb_tma_load_1d(ring + (size_t)slot * TILE_ELEMS, src + (size_t)(ts + t) * TILE_ELEMS,
+                               TILE_BYTES, &full_bar[slot]);
+            }
+        }
+
+        float npos[TI][3], mi[TI];
+        int own_tile[TI];
+        bool suspect = false;
+#pragma unroll
+        for (int t = 0; t < TI; ++t) {
+            const long long b = P.tgt_base + (long long)it * ITILE + tid + t * BLOCK;
+            own_tile[t] = (int)(b / NB_TILE);
+            const float* tb = src + (size_t)(b / NB_TILE) * TILE_ELEMS + (b % NB_TILE);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) npos[t][d] = (d < D) ? -tb[d * NB_TILE] : 0.f;
+            mi[t] = tb[D * NB_TILE];
+            suspect |= P.suspect[it * ITILE + tid + t * BLOCK] != 0;
+        }
+        const bool warp_suspect = __any_sync(0xffffffffu, suspect) != 0;
+        double accd[TI][3];
+#pragma unroll
+        for (int t = 0; t < TI; ++t)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) accd[t][d] = 0.0;
+
+        for (int t = 0; t < ntl; ++t) {
+            if (tid == 0 && t + NB_STAGES - 1 < ntl) {
+                const unsigned k = kt + t + NB_STAGES - 1;
+                const int slot = k % NB_STAGES;
+                nb_mbar_wait(&empty_bar[slot], ((k / NB_STAGES) & 1u) ^ 1u);
+                nb_mbar_expect_tx(&full_bar[slot], TILE_BYTES);
+                nb_tma_load_1d(ring + (size_t)slot * TILE_ELEMS,
+                               src + (size_t)(ts + t + NB_STAGES - 1) * TILE_ELEMS, TILE_BYTES,
+                               &full_bar[slot]);
+            }
+            const unsigned k = kt + t;
+            const int slot = k % NB_STAGES;
+            nb_mbar_wait(&full_bar[slot], (k / NB_STAGES) & 1u);
+            const float* stage = ring + (size_t)slot * TILE_ELEMS;
+            float2 a[TI][3];
+            if (sym) {
+                float* wout = bout_all + ((size_t)bbuf * NWARPS + warp) * (D * NB_TILE);
+                if (warp_suspect) nb_tile_f32_sym<D, NB_EXACT>(stage, P.cutoff, npos, mi, a, scr, wout, lane);
+                else nb_tile_f32_sym<D, NB_PLAIN>(stage, P.cutoff, npos, mi, a, scr, wout, lane);
+            } else {
+                bool exact_tile = warp_suspect;
+#pragma unroll
+                for (int tt = 0; tt < TI; ++tt) exact_tile |= (ts + t == own_tile[tt]);
+                if (exact_tile) nb_tile_f32<D, TI, 1, NB_EXACT, 1>(stage, 0, P.cutoff, npos, a);
+                else nb_tile_f32<D, TI, 1, NB_PLAIN, 1>(stage, 0, P.cutoff, npos, a);
+            }
+#pragma unroll
+            for (int tt = 0; tt < TI; ++tt)
+#pragma unroll
+                for (int d = 0; d < D; ++d) accd[tt][d] += (double)(a[tt][d].x + a[tt][d].y);
+            __syncwarp();
+            if (lane == 0) nb_mbar_arrive(&empty_bar[slot]);
+            if (sym) {
+                // CTA-wide sum of the eight warps' tile buffers, one FP64 atomic per (source, component);
+                // the reaction on source j is MINUS sum_i (m_i / r^4) d_ij
+                __syncthreads();
+                const float* bb = bout_all + (size_t)bbuf * NWARPS * (D * NB_TILE);
+                const long long lj = (long long)(ts + t) * NB_TILE + tid - P.tgt_base;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int w = 0; w < NWARPS; ++w) v += bb[(size_t)w * (D * NB_TILE) + d * NB_TILE + tid];
+                    atomicAdd(&P.acc[(size_t)d * P.tpad + lj], -(double)v);
+                }
+                bbuf ^= 1;
+            }
+        }
+        kt += ntl;
+
+#pragma unroll
+        for (int t = 0; t < TI; ++t)
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const int li = it * ITILE + tid + t * BLOCK;
+                atomicAdd(&P.acc[(size_t)d * P.tpad + li], accd[t][d]);
+            }
+    }
+
+    if (tid == 0) {
+        __threadfence();
+        const unsigned e = atomicAdd(&P.sched[1], 1u);
+        if (e + 1u == gridDim.x) {
+            P.sched[0] = 0u;
+            P.sched[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+// Epilogue of a pass whose accumulators are complete only when the whole pass is (symmetric
+// pass): the same arithmetic as the fused epilogue of nb_force_kernel.
+//   forces:  F_i = -(G m_i) S_i                                  methods.cpp:125-131
+//   step:    v += (F/m) dt ; x += v dt ; new source row           methods.cpp:436, :448
+template <int D, typename real>
+__global__ void __launch_bounds__(256) nb_finish_kernel(const NbForceParams P) {
+    constexpr int NP = D + 1;
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= P.tpad) return;
+    double S[3];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        double* ap = &P.acc[(size_t)d * P.tpad + li];
+        S[d] = *ap * P.acc_scale;
+        *ap = 0.0;                                   // self-clean for the next pass
+    }
+    if (li >= P.n_local) return;
+    const double m = P.mass[li];
+    const double gm = P.G * m;
+    double F[3];
+#pragma unroll
+    for (int d = 0; d < D; ++d) F[d] = -(gm * S[d]);
+    if (P.mode == 0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) P.forces[(size_t)li * D + d] = F[d];
+        return;
+    }
+    const long long b = P.tgt_base + li;
+    const size_t off0 = (size_t)(b / NB_TILE) * (NB_TILE * NP) + (b % NB_TILE);
+    real* nb = static_cast<real*>(P.src_next) + off0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        double v = P.vel[(size_t)d * P.tpad + li];
+        double x = P.pos[(size_t)d * P.tpad + li];
+        v += (F[d] / m) * P.dt;
+        x += v * P.dt;
+        P.vel[(size_t)d * P.tpad + li] = v;
+        P.pos[(size_t)d * P.tpad + li] = x;
+        const real xs = (real)(x * P.pos_scale);
+        nb[d * NB_TILE] = xs;
+        for (int pr = 0; pr < P.n_peers; ++pr)
+            static_cast<real*>(P.peer_next[pr])[off0 + (size_t)d * NB_TILE] = xs;
+    }
+}

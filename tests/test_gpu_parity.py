@@ -418,3 +418,34 @@ def test_fp32_scales_come_from_the_device_side_bounds(pkg, oracle):
 def test_measured_fp32_peak_is_plausible(pkg):
     t = pkg.measure_fp32_peak(0)
     assert 40.0 <= t <= 80.0, t      # B200: 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4 nominal
+
+
+# ------------------------------------------------------------------ pair-symmetric pass
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("n", [1, 300, 1024, 5000, 9473])
+@pytest.mark.parametrize("seg_tiles", [0, 1, 5])
+def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, seg_tiles):
+    """Each unordered pair evaluated once (both reactions) must reproduce the ordered-pair pass and
+    the oracle: forces, and a few fused steps through the finish kernel; ragged sizes, duplicates."""
+    b = pkg.generators.uniform_cube(n, dim, seed=31 + n)
+    if n >= 300:
+        b[17, :dim] = b[3, :dim]                       # exact duplicate
+        b[101, :dim] = b[100, :dim] + 2e-6             # pair under the cut-off (r^2 = 1.2e-11 < 1e-10)
+    b = pkg.generators.round_to_float(b)
+    opts = {"detect": 1, "seg_tiles": seg_tiles}
+    f_sym = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32, options=dict(opts, symmetric=1))
+    f_ord = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32, options=dict(opts, symmetric=0))
+    assert_fp32_parity(pkg, oracle, f_sym, b, f"symmetric n={n}")
+    assert_fp32_parity(pkg, oracle, f_ord, b, f"ordered n={n}")
+    with pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as ctx:
+        ctx.set_option("detect", 1)
+        ctx.set_option("symmetric", 1)
+        ctx.upload(b)
+        ctx.forces()
+        assert "pair-symmetric" in ctx.plan
+        ctx.step(1e-5, 3)
+        got = b.copy()
+        ctx.download(got)
+    want = pkg.brute_force_cuda_simulate(b, 1e-5, 3, pkg.NB200_FP32, options=dict(opts, symmetric=0))
+    scale = np.abs(want[:, :2 * dim]).max()
+    assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= 2e-6 * scale
