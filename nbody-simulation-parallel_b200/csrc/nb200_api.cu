@@ -195,7 +195,7 @@ struct nb200_ctx {
     unsigned long long epoch = 0;        // uploads so far (published on the epoch flags)
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 4;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
@@ -285,9 +285,12 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
             CK(cudaFuncSetAttribute((const void*)pick_kernel(D, ctx->f64, v, fl != 0),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem_bytes(D, ctx->f64)));
-    if (!ctx->f64)
-        CK(cudaFuncSetAttribute((const void*)(D == 3 ? nb_force_sym_kernel<3> : nb_force_sym_kernel<2>),
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nb_sym_smem_bytes(D)));
+    if (!ctx->f64) {
+        const void* ks[2] = {D == 3 ? (const void*)nb_force_sym_kernel<3, 4, 256> : (const void*)nb_force_sym_kernel<2, 4, 256>,
+                             D == 3 ? (const void*)nb_force_sym_kernel<3, 8, 128> : (const void*)nb_force_sym_kernel<2, 8, 128>};
+        CK(cudaFuncSetAttribute(ks[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nb_sym_smem_bytes(D, 256)));
+        CK(cudaFuncSetAttribute(ks[1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nb_sym_smem_bytes(D, 128)));
+    }
     return NB200_OK;
 }
 
@@ -587,12 +590,17 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     Q.own_tile_end = own_end;
     Q.total_units = s.unit_prefix_host[n_itiles];
     Q.cutoff = (float)(cutoff * ctx->pos_scale * ctx->pos_scale);
-    const void* kfn = D == 3 ? (const void*)nb_force_sym_kernel<3> : (const void*)nb_force_sym_kernel<2>;
+    // two register-block shapes of the same 1024-target i-tile: 4 targets x 256 threads, 8 x 128
+    const int ti = ctx->opt_sym_ti == 8 ? 8 : 4;
+    const int block = NB_SYM_ITILE / ti;
+    typedef void (*SymKernel)(const NbSymParams);
+    const SymKernel kfn = D == 3 ? (ti == 8 ? nb_force_sym_kernel<3, 8, 128> : nb_force_sym_kernel<3, 4, 256>)
+                                 : (ti == 8 ? nb_force_sym_kernel<2, 8, 128> : nb_force_sym_kernel<2, 4, 256>);
+    const size_t smem = nb_sym_smem_bytes(D, block);
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, NB_SYM_BLOCK, nb_sym_smem_bytes(D)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kfn, block, smem));
     const int grid = std::min(std::max(1, nb) * s.sms, Q.total_units);
-    if (D == 3) nb_force_sym_kernel<3><<<grid, NB_SYM_BLOCK, nb_sym_smem_bytes(D), s.compute>>>(Q);
-    else nb_force_sym_kernel<2><<<grid, NB_SYM_BLOCK, nb_sym_smem_bytes(D), s.compute>>>(Q);
+    kfn<<<grid, block, smem, s.compute>>>(Q);
     CK(cudaGetLastError());
     NbForceParams P = base_params(ctx, s, mode, G, cutoff, dt, cur, Handshake());
     const int fb = (s.tpad + 255) / 256;
@@ -602,9 +610,9 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     ctx->launches += 2;
     char buf[256];
     snprintf(buf, sizeof buf,
-             "%s: fp32 dim=%d n=%zu shards=1 pair-symmetric(TI=4,block=256,itile=1024) seg_tiles=%d i-tiles=%d "
+             "%s: fp32 dim=%d n=%zu shards=1 pair-symmetric(TI=%d,block=%d,itile=1024) seg_tiles=%d i-tiles=%d "
              "units=%d grid=%d tiles=%lld cutoff=grid-prepass(plain|exact) + finish kernel",
-             mode ? "step" : "forces", D, ctx->n, seg, n_itiles, Q.total_units, grid, ctx->ntiles);
+             mode ? "step" : "forces", D, ctx->n, ti, block, seg, n_itiles, Q.total_units, grid, ctx->ntiles);
     ctx->plan = buf;
     return NB200_OK;
 }
@@ -969,6 +977,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "trace")) ctx->opt_trace = value != 0;
     else if (!strcmp(key, "detect")) ctx->opt_detect = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "symmetric")) ctx->opt_symmetric = value < 0 ? -1 : (value != 0);
+    else if (!strcmp(key, "sym_ti")) ctx->opt_sym_ti = value == 8 ? 8 : 4;
     else if (!strcmp(key, "exchange")) {
         if (value == 1 && !ctx->p2p_ready) return fail(ctx, NB200_ESTATE, "peer-store exchange is not attached");
         if (value == 0 && ctx->rank_mode && ctx->world > 1 && !ctx->detached && !ctx->shards[0].comm_nccl)

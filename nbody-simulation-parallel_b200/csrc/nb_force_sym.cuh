@@ -21,9 +21,7 @@
 #pragma once
 #include "nb_force.cuh"
 
-#define NB_SYM_TI 4
-#define NB_SYM_BLOCK 256
-#define NB_SYM_ITILE (NB_SYM_TI * NB_SYM_BLOCK)     // 1024 targets = 4 source tiles
+#define NB_SYM_ITILE 1024                           // targets per i-tile = TI * BLOCK = 4 source tiles
 #define NB_SYM_ROW 14                               // floats per lane row of the transpose scratch (12 used):
                                                     // 14 makes the STS.64 writes and the column reads bank-conflict free
 
@@ -43,11 +41,11 @@ struct NbSymParams {
     float cutoff;                // scaled r^2 cut-off
 };
 
-static inline size_t nb_sym_smem_bytes(int dim) {
+static inline size_t nb_sym_smem_bytes(int dim, int block) {
     const size_t ring = (size_t)NB_STAGES * NB_TILE * (dim + 1) * sizeof(float);
     const size_t bars = 2 * NB_STAGES * sizeof(uint64_t) + 16;
-    const size_t scr = (size_t)(NB_SYM_BLOCK / 32) * 2 * 32 * NB_SYM_ROW * sizeof(float);
-    const size_t bout = (size_t)2 * (NB_SYM_BLOCK / 32) * dim * NB_TILE * sizeof(float);
+    const size_t scr = (size_t)(block / 32) * 2 * 32 * NB_SYM_ROW * sizeof(float);
+    const size_t bout = (size_t)2 * (block / 32) * dim * NB_TILE * sizeof(float);
     return ring + bars + scr + bout;
 }
 
@@ -55,18 +53,18 @@ static inline size_t nb_sym_smem_bytes(int dim) {
 //   a[t][d]  += sum_j (m_j / r^4) d_ij          (this tile's FP32 partial of the target sums)
 //   wout[d][j] = sum over the warp's 128 targets of (m_i / r^4) d_ij   (NOT yet negated)
 // scr = this warp's two 32 x NB_SYM_ROW transpose buffers; lane = tid & 31.
-template <int D, int MODE>
+template <int D, int TI, int MODE>
 __device__ __forceinline__ void nb_tile_f32_sym(const float* __restrict__ stage, float cutoff,
-                                                const float (&npos)[NB_SYM_TI][3],
-                                                const float (&mi)[NB_SYM_TI],
-                                                float2 (&a)[NB_SYM_TI][3], float* __restrict__ scr,
+                                                const float (&npos)[TI][3],
+                                                const float (&mi)[TI],
+                                                float2 (&a)[TI][3], float* __restrict__ scr,
                                                 float* __restrict__ wout, int lane) {
     const float4* sx = reinterpret_cast<const float4*>(stage);
     const float4* sy = sx + NB_TILE / 4;
     const float4* sz = sy + NB_TILE / 4;                      // D == 3 only
     const float4* sm = sx + D * (NB_TILE / 4);
 #pragma unroll
-    for (int t = 0; t < NB_SYM_TI; ++t)
+    for (int t = 0; t < TI; ++t)
 #pragma unroll
         for (int d = 0; d < 3; ++d) a[t][d] = make_float2(0.f, 0.f);
     const float inf = __int_as_float(0x7f800000);
@@ -108,7 +106,7 @@ __device__ __forceinline__ void nb_tile_f32_sym(const float* __restrict__ stage,
 #pragma unroll
             for (int d = 0; d < 3; ++d) b[h][d] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < NB_SYM_TI; ++t) {
+            for (int t = 0; t < TI; ++t) {
                 const float2 dx = __fadd2_rn(xs, make_float2(npos[t][0], npos[t][0]));
                 const float2 dy = __fadd2_rn(ys, make_float2(npos[t][1], npos[t][1]));
                 float2 r2 = __fmul2_rn(dx, dx);
@@ -153,12 +151,11 @@ __device__ __forceinline__ void nb_tile_f32_sym(const float* __restrict__ stage,
     __syncwarp();
 }
 
-template <int D>
-__global__ void __launch_bounds__(NB_SYM_BLOCK, 2) nb_force_sym_kernel(const NbSymParams P) {
+template <int D, int TI, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? 2 : 3) nb_force_sym_kernel(const NbSymParams P) {
     constexpr int NP = D + 1;
-    constexpr int TI = NB_SYM_TI;
-    constexpr int BLOCK = NB_SYM_BLOCK;
     constexpr int ITILE = NB_SYM_ITILE;
+    static_assert(TI * BLOCK == ITILE, "i-tile is 1024 targets");
     constexpr int TILE_ELEMS = NB_TILE * NP;
     constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(float);
     constexpr int NWARPS = BLOCK / 32;
@@ -265,8 +262,8 @@ __global__ void __launch_bounds__(NB_SYM_BLOCK, 2) nb_force_sym_kernel(const NbS
             float2 a[TI][3];
             if (sym) {
                 float* wout = bout_all + ((size_t)bbuf * NWARPS + warp) * (D * NB_TILE);
-                if (warp_suspect) nb_tile_f32_sym<D, NB_EXACT>(stage, P.cutoff, npos, mi, a, scr, wout, lane);
-                else nb_tile_f32_sym<D, NB_PLAIN>(stage, P.cutoff, npos, mi, a, scr, wout, lane);
+                if (warp_suspect) nb_tile_f32_sym<D, TI, NB_EXACT>(stage, P.cutoff, npos, mi, a, scr, wout, lane);
+                else nb_tile_f32_sym<D, TI, NB_PLAIN>(stage, P.cutoff, npos, mi, a, scr, wout, lane);
             } else {
                 bool exact_tile = warp_suspect;
 #pragma unroll
@@ -285,13 +282,15 @@ __global__ void __launch_bounds__(NB_SYM_BLOCK, 2) nb_force_sym_kernel(const NbS
                 // the reaction on source j is MINUS sum_i (m_i / r^4) d_ij
                 __syncthreads();
                 const float* bb = bout_all + (size_t)bbuf * NWARPS * (D * NB_TILE);
-                const long long lj = (long long)(ts + t) * NB_TILE + tid - P.tgt_base;
+                for (int j = tid; j < NB_TILE; j += BLOCK) {
+                    const long long lj = (long long)(ts + t) * NB_TILE + j - P.tgt_base;
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    float v = 0.f;
+                    for (int d = 0; d < D; ++d) {
+                        float v = 0.f;
 #pragma unroll
-                    for (int w = 0; w < NWARPS; ++w) v += bb[(size_t)w * (D * NB_TILE) + d * NB_TILE + tid];
-                    atomicAdd(&P.acc[(size_t)d * P.tpad + lj], -(double)v);
+                        for (int w = 0; w < NWARPS; ++w) v += bb[(size_t)w * (D * NB_TILE) + d * NB_TILE + j];
+                        atomicAdd(&P.acc[(size_t)d * P.tpad + lj], -(double)v);
+                    }
                 }
                 bbuf ^= 1;
             }

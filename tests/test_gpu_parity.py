@@ -119,7 +119,7 @@ def test_close_pair_prepass_matches_tracked_path(pkg, oracle, prec, dim):
     got = {}
     for detect in (1, 0):
         for variant in (0, 4):
-            f = pkg.brute_force_cuda_n_body(b, prec, options={"detect": detect, "variant": variant})
+            f = pkg.brute_force_cuda_n_body(b, prec, options={"detect": detect, "variant": variant, "symmetric": 0})
             assert np.all(np.isfinite(f))
             if prec == 64:
                 e = rel(pkg, f, ref)
@@ -128,6 +128,13 @@ def test_close_pair_prepass_matches_tracked_path(pkg, oracle, prec, dim):
                 assert_fp32_parity(pkg, oracle, f, b, f"detect={detect} variant={variant}")
             got[(detect, variant)] = f
     assert rel(pkg, got[(1, 0)], got[(0, 0)]).max() <= (1e-13 if prec == 64 else 1e-6)
+    if prec == 32:
+        # the pair-symmetric pass (the FP32 default once the pre-pass is on) sums the reactions in a
+        # different order: held to the same kappa-aware criterion, not to bitwise-close agreement
+        for ti in (4, 8):
+            f = pkg.brute_force_cuda_n_body(b, prec, options={"detect": 1, "symmetric": 1, "sym_ti": ti})
+            assert np.all(np.isfinite(f))
+            assert_fp32_parity(pkg, oracle, f, b, f"pair-symmetric TI={ti}")
     # and through the fused step: same trajectory with and without the pre-pass
     a1 = pkg.brute_force_cuda_simulate(b, 1e-6, 5, prec, options={"detect": 1})
     a0 = pkg.brute_force_cuda_simulate(b, 1e-6, 5, prec, options={"detect": 0})
@@ -423,8 +430,8 @@ def test_measured_fp32_peak_is_plausible(pkg):
 # ------------------------------------------------------------------ pair-symmetric pass
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("n", [1, 300, 1024, 5000, 9473])
-@pytest.mark.parametrize("seg_tiles", [0, 1, 5])
-def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, seg_tiles):
+@pytest.mark.parametrize("seg_tiles,sym_ti", [(0, 4), (1, 4), (5, 8), (0, 8)])
+def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, seg_tiles, sym_ti):
     """Each unordered pair evaluated once (both reactions) must reproduce the ordered-pair pass and
     the oracle: forces, and a few fused steps through the finish kernel; ragged sizes, duplicates."""
     b = pkg.generators.uniform_cube(n, dim, seed=31 + n)
@@ -433,16 +440,17 @@ def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, seg_tiles
         b[101, :dim] = b[100, :dim] + 2e-6             # pair under the cut-off (r^2 = 1.2e-11 < 1e-10)
     b = pkg.generators.round_to_float(b)
     opts = {"detect": 1, "seg_tiles": seg_tiles}
-    f_sym = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32, options=dict(opts, symmetric=1))
+    f_sym = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32, options=dict(opts, symmetric=1, sym_ti=sym_ti))
     f_ord = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32, options=dict(opts, symmetric=0))
     assert_fp32_parity(pkg, oracle, f_sym, b, f"symmetric n={n}")
     assert_fp32_parity(pkg, oracle, f_ord, b, f"ordered n={n}")
     with pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as ctx:
         ctx.set_option("detect", 1)
         ctx.set_option("symmetric", 1)
+        ctx.set_option("sym_ti", sym_ti)
         ctx.upload(b)
         ctx.forces()
-        assert "pair-symmetric" in ctx.plan
+        assert f"pair-symmetric(TI={sym_ti}" in ctx.plan
         ctx.step(1e-5, 3)
         got = b.copy()
         ctx.download(got)
