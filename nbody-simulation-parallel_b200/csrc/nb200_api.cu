@@ -156,10 +156,15 @@ struct Shard {
     unsigned* grid_counts = nullptr;
     unsigned grid_cap = 0;
     unsigned char* suspect = nullptr;                 // [tpad]
-    // pair-symmetric pass: first flat unit index of every own i-tile (device copy + the host image it mirrors)
-    int* unit_prefix = nullptr;
-    std::vector<int> unit_prefix_host;
-    int sym_seg_tiles = 0;
+    // pair-symmetric pass (nb_force_sym.cuh): work list, global-index accumulators, counters
+    NbSymRow* sym_rows = nullptr;
+    int* sym_prefix = nullptr;
+    int sym_rows_cap = 0;
+    std::vector<NbSymRow> sym_rows_host;
+    std::vector<int> sym_prefix_host;
+    int sym_key_seg = 0, sym_key_world = 0;
+    double* gacc = nullptr;                           // [3][nalloc]
+    unsigned* sym_done = nullptr;                     // [2] push / finish CTA counters
     // fused NVLink exchange (peer stores from the epilogue + flag handshake)
     unsigned long long* flags = nullptr;              // [2*kMaxWorldP2P]: step flags, then epoch flags, by writer rank
     int n_peers = 0;
@@ -170,6 +175,8 @@ struct Shard {
 };
 
 constexpr int kMaxWorldP2P = NB_MAX_PEERS + 1;
+constexpr int kSymMaxSlots = kMaxWorldP2P / 2;      // senders of reaction sums per rank: floor(world / 2)
+constexpr size_t kFlagsBytes = 256;                 // 3 * kMaxWorldP2P flag words, padded
 
 }  // namespace
 
@@ -193,6 +200,7 @@ struct nb200_ctx {
     unsigned long long step_index = 0;   // steps issued since creation (the published flag value)
     unsigned long long epoch_base = 0;   // step_index at the last upload
     unsigned long long epoch = 0;        // uploads so far (published on the epoch flags)
+    std::vector<unsigned long long> acc_seq_issued;   // per driven shard: pair-symmetric passes with a reaction exchange so far
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
     int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 4;
@@ -273,10 +281,24 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
         CK(cudaMalloc(&s.grid_counts, (size_t)cap * sizeof(unsigned)));
         CK(cudaMalloc(&s.suspect, tp));
         CK(cudaMemset(s.suspect, 1, tp));
-        CK(cudaMalloc(&s.unit_prefix, (tp / NB_SYM_ITILE + 2) * sizeof(int)));
+        if (!ctx->f64) {
+            // rows: per own i-tile one ordered + one triangular row, plus one row per cross-shard block
+            s.sym_rows_cap = (int)(tp / NB_SYM_ITILE + 1) * (2 + kSymMaxSlots);
+            CK(cudaMalloc(&s.sym_rows, (size_t)s.sym_rows_cap * sizeof(NbSymRow)));
+            CK(cudaMalloc(&s.sym_prefix, (size_t)(s.sym_rows_cap + 1) * sizeof(int)));
+            CK(cudaMalloc(&s.gacc, 3 * (size_t)ctx->nalloc * sizeof(double)));
+            CK(cudaMemset(s.gacc, 0, 3 * (size_t)ctx->nalloc * sizeof(double)));
+            CK(cudaMalloc(&s.sym_done, 2 * sizeof(unsigned)));
+            CK(cudaMemset(s.sym_done, 0, 2 * sizeof(unsigned)));
+        }
     }
-    CK(cudaMalloc(&s.flags, 2 * kMaxWorldP2P * sizeof(unsigned long long)));
-    CK(cudaMemset(s.flags, 0, 2 * kMaxWorldP2P * sizeof(unsigned long long)));
+    {
+        // flag words (step, epoch, reaction-sum pass: one per writer rank each) and, behind them in the
+        // SAME allocation (one IPC handle), the receive slots of the pair-symmetric pass
+        const size_t slots = ctx->f64 ? 0 : (size_t)kSymMaxSlots * 3 * (size_t)ctx->tiles_per_shard * NB_TILE * sizeof(double);
+        CK(cudaMalloc(&s.flags, kFlagsBytes + slots));
+        CK(cudaMemset(s.flags, 0, kFlagsBytes));
+    }
     CK(cudaMalloc(&s.sched, 2 * sizeof(unsigned)));
     CK(cudaMemset(s.sched, 0, 2 * sizeof(unsigned)));
     // opt in to the dynamic shared memory of every variant once
@@ -307,7 +329,7 @@ void free_shard(Shard& s) {
         }
     }
     cudaFree(s.flags);
-    cudaFree(s.grid_keys); cudaFree(s.grid_counts); cudaFree(s.suspect); cudaFree(s.unit_prefix);
+    cudaFree(s.grid_keys); cudaFree(s.grid_counts); cudaFree(s.suspect); cudaFree(s.sym_rows); cudaFree(s.sym_prefix); cudaFree(s.gacc); cudaFree(s.sym_done);
     for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
     cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
     cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.bounds); cudaFree(s.tile_done); cudaFree(s.sched);
@@ -551,44 +573,93 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
     return NB200_OK;
 }
 
-// ---- pair-symmetric pass (FP32, one shard owning all sources): see nb_force_sym.cuh
-bool use_symmetric(const nb200_ctx* ctx) {
-    if (ctx->f64 || ctx->world != 1 || !use_detect(ctx)) return false;
-    return ctx->opt_symmetric != 0;
+// ---- pair-symmetric pass (FP32): see nb_force_sym.cuh.  One shard: every pair once.  Several
+// shards (fused NVLink exchange attached): rank g also evaluates the blocks (g, g+off) for
+// off = 1 .. floor((G-1)/2) and, for even G, half of the block against the opposite rank; the
+// reaction sums on the other rank's bodies are pushed into that rank's receive slots.
+bool use_symmetric(const nb200_ctx* ctx, bool stepping) {
+    if (ctx->f64 || !use_detect(ctx) || ctx->opt_symmetric == 0) return false;
+    if (ctx->world == 1) return true;
+    // cross-rank flavour: only inside nb200_step (nb200_forces stays a rank-local call)
+    return stepping && !ctx->detached && ctx->p2p_ready && ctx->exchange == 1 && ctx->world <= kMaxWorldP2P;
 }
 
-// symmetric force kernel over the own x own block, then the finish kernel (forces or integrate)
-int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff, double dt, int cur) {
-    const int D = ctx->dim;
-    const int tiles_per_itile = NB_SYM_ITILE / NB_TILE;
-    const int own_begin = (int)s.tile_lo, own_end = (int)s.tile_hi;
-    const int n_itiles = (own_end - own_begin + tiles_per_itile - 1) / tiles_per_itile;
-    int seg = ctx->opt_seg_tiles;
-    if (seg <= 0) seg = (own_end - own_begin) <= 1024 ? 8 : (own_end - own_begin) <= 2048 ? 16 : 32;
-    if ((int)s.unit_prefix_host.size() != n_itiles + 1 || s.sym_seg_tiles != seg) {
-        s.unit_prefix_host.assign(n_itiles + 1, 0);
-        for (int it = 0; it < n_itiles; ++it) {
-            const int above = own_end - std::min(own_end, own_begin + (it + 1) * tiles_per_itile);
-            s.unit_prefix_host[it + 1] = s.unit_prefix_host[it] + 1 + (above + seg - 1) / seg;
-        }
-        s.sym_seg_tiles = seg;
-        CK(cudaMemcpyAsync(s.unit_prefix, s.unit_prefix_host.data(), (n_itiles + 1) * sizeof(int),
-                           cudaMemcpyHostToDevice, s.compute));
+int peer_index(const Shard& s, int rank) {
+    for (int p = 0; p < s.n_peers; ++p)
+        if (s.peer_rank[p] == rank) return p;
+    return -1;
+}
+
+int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg, bool cross) {
+    const int G = cross ? ctx->world : 1;
+    if (!s.sym_rows_host.empty() && s.sym_key_seg == seg && s.sym_key_world == G) return NB200_OK;
+    const int tpi = NB_SYM_ITILE / NB_TILE;                      // source tiles per i-tile
+    const int lo = (int)s.tile_lo, hi = (int)s.tile_hi;
+    const int T = (int)ctx->tiles_per_shard;
+    const int n_it = (hi - lo + tpi - 1) / tpi;
+    std::vector<NbSymRow>& rows = s.sym_rows_host;
+    rows.clear();
+    for (int it = 0; it < n_it; ++it) {
+        const int d0 = lo + it * tpi, d1 = std::min(d0 + tpi, hi);
+        rows.push_back(NbSymRow{it, d0, d1, 0});                 // the i-tile against itself: ordered pairs
+        if (d1 < hi) rows.push_back(NbSymRow{it, d1, hi, NB_ROW_SYM});
     }
+    if (G > 1) {
+        const int g = s.rank;
+        for (int off = 1; off <= (G - 1) / 2; ++off) {
+            const int h = (g + off) % G;
+            for (int it = 0; it < n_it; ++it) rows.push_back(NbSymRow{it, h * T, (h + 1) * T, NB_ROW_SYM});
+        }
+        if (G % 2 == 0) {
+            // the block against the opposite rank is split between the two: the lower rank takes its own
+            // first half of i-tiles against all of the other's bodies, the higher rank all of its targets
+            // against the lower rank's remaining bodies
+            const int o = (g + G / 2) % G, half = n_it / 2;
+            if (g < o) {
+                for (int it = 0; it < half; ++it) rows.push_back(NbSymRow{it, o * T, (o + 1) * T, NB_ROW_SYM});
+            } else {
+                const int b0 = std::min(o * T + half * tpi, (o + 1) * T);
+                if (b0 < (o + 1) * T)
+                    for (int it = 0; it < n_it; ++it) rows.push_back(NbSymRow{it, b0, (o + 1) * T, NB_ROW_SYM});
+            }
+        }
+    }
+    if ((int)rows.size() > s.sym_rows_cap) return fail(ctx, NB200_ESTATE, "symmetric work list overflow");
+    s.sym_prefix_host.assign(rows.size() + 1, 0);
+    for (size_t r = 0; r < rows.size(); ++r)
+        s.sym_prefix_host[r + 1] = s.sym_prefix_host[r] + (rows[r].t_end - rows[r].t_begin + seg - 1) / seg;
+    s.sym_key_seg = seg;
+    s.sym_key_world = G;
+    CK(cudaMemcpyAsync(s.sym_rows, rows.data(), rows.size() * sizeof(NbSymRow), cudaMemcpyHostToDevice, s.compute));
+    CK(cudaMemcpyAsync(s.sym_prefix, s.sym_prefix_host.data(), s.sym_prefix_host.size() * sizeof(int),
+                       cudaMemcpyHostToDevice, s.compute));
+    return NB200_OK;
+}
+
+// symmetric force kernel, [push of the reaction sums to their owners], finish kernel (forces or integrate)
+int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff, double dt, int cur,
+                     const Handshake& hs = Handshake()) {
+    const int D = ctx->dim;
+    const bool cross = ctx->world > 1;
+    const int W = ctx->world;
+    const int tiles = (int)ctx->tiles_per_shard;
+    int seg = ctx->opt_seg_tiles;
+    if (seg <= 0) seg = tiles * (cross ? W : 1) <= 1024 ? 8 : tiles * (cross ? W : 1) <= 2048 ? 16 : 32;
+    if (int rc = build_sym_rows(ctx, s, seg, cross)) return rc;
     NbSymParams Q;
     memset(&Q, 0, sizeof Q);
     Q.src = static_cast<const float*>(s.src[cur]);
-    Q.acc = s.acc;
+    Q.gacc = s.gacc;
+    Q.gstride = (size_t)ctx->nalloc;
     Q.sched = s.sched;
-    Q.unit_prefix = s.unit_prefix;
+    Q.rows = s.sym_rows;
+    Q.row_prefix = s.sym_prefix;
     Q.suspect = s.suspect;
     Q.tgt_base = s.tgt_base;
-    Q.tpad = s.tpad;
-    Q.n_itiles = n_itiles;
+    Q.own_count = tiles * NB_TILE;
+    Q.n_rows = (int)s.sym_rows_host.size();
     Q.seg_tiles = seg;
-    Q.own_tile_begin = own_begin;
-    Q.own_tile_end = own_end;
-    Q.total_units = s.unit_prefix_host[n_itiles];
+    Q.total_units = s.sym_prefix_host.back();
     Q.cutoff = (float)(cutoff * ctx->pos_scale * ctx->pos_scale);
     // two register-block shapes of the same 1024-target i-tile: 4 targets x 256 threads, 8 x 128
     const int ti = ctx->opt_sym_ti == 8 ? 8 : 4;
@@ -602,18 +673,61 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     const int grid = std::min(std::max(1, nb) * s.sms, Q.total_units);
     kfn<<<grid, block, smem, s.compute>>>(Q);
     CK(cudaGetLastError());
-    NbForceParams P = base_params(ctx, s, mode, G, cutoff, dt, cur, Handshake());
+    ctx->launches++;
+
+    NbSymFinish F;
+    memset(&F, 0, sizeof F);
+    F.gacc = s.gacc;
+    F.gstride = (size_t)ctx->nalloc;
+    F.count = tiles * NB_TILE;
+    F.done = s.sym_done + 1;
+    if (cross) {
+        const int n_ex = W / 2;                     // ranks this one sends to == ranks it receives from
+        const unsigned long long seq = ++ctx->acc_seq_issued[&s - &ctx->shards[0]];
+        NbSymPush U;
+        memset(&U, 0, sizeof U);
+        U.gacc = s.gacc;
+        U.gstride = (size_t)ctx->nalloc;
+        U.count = tiles * NB_TILE;
+        U.seq = seq;
+        U.done = s.sym_done;
+        const size_t slot_doubles = (size_t)3 * tiles * NB_TILE;
+        for (int off = 1; off <= n_ex; ++off) {
+            const int h = (s.rank + off) % W, q = (s.rank - off + W) % W;
+            const int ph = peer_index(s, h), pq = peer_index(s, q);
+            if (ph < 0 || pq < 0) return fail(ctx, NB200_ESTATE, "peer %d/%d of rank %d is not attached", h, q, s.rank);
+            const int k = U.n_dst++;
+            U.body_begin[k] = (long long)h * tiles * NB_TILE;
+            U.dst_slot[k] = reinterpret_cast<double*>(reinterpret_cast<char*>(s.peer_flags[ph]) + kFlagsBytes) +
+                            (size_t)(off - 1) * slot_doubles;
+            U.dst_flag[k] = s.peer_flags[ph] + 2 * kMaxWorldP2P + s.rank;
+            F.slot[F.n_src] = reinterpret_cast<const double*>(reinterpret_cast<const char*>(s.flags) + kFlagsBytes) +
+                              (size_t)(off - 1) * slot_doubles;
+            F.flag[F.n_src] = s.flags + 2 * kMaxWorldP2P + q;
+            F.n_src++;
+        }
+        F.seq = seq;
+        const int pb = std::min(4 * s.sms, (int)(((long long)U.count * D * U.n_dst + 255) / 256));
+        if (D == 3) nb_sym_push_kernel<3><<<pb, 256, 0, s.compute>>>(U);
+        else nb_sym_push_kernel<2><<<pb, 256, 0, s.compute>>>(U);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    NbForceParams P = base_params(ctx, s, mode, G, cutoff, dt, cur, hs);
     const int fb = (s.tpad + 255) / 256;
-    if (D == 3) nb_finish_kernel<3, float><<<fb, 256, 0, s.compute>>>(P);
-    else nb_finish_kernel<2, float><<<fb, 256, 0, s.compute>>>(P);
+    if (D == 3) nb_finish_kernel<3, float><<<fb, 256, 0, s.compute>>>(P, F);
+    else nb_finish_kernel<2, float><<<fb, 256, 0, s.compute>>>(P, F);
     CK(cudaGetLastError());
-    ctx->launches += 2;
-    char buf[256];
-    snprintf(buf, sizeof buf,
-             "%s: fp32 dim=%d n=%zu shards=1 pair-symmetric(TI=%d,block=%d,itile=1024) seg_tiles=%d i-tiles=%d "
-             "units=%d grid=%d tiles=%lld cutoff=grid-prepass(plain|exact) + finish kernel",
-             mode ? "step" : "forces", D, ctx->n, ti, block, seg, n_itiles, Q.total_units, grid, ctx->ntiles);
-    ctx->plan = buf;
+    ctx->launches++;
+    if (&s == &ctx->shards[0]) {
+        char buf[320];
+        snprintf(buf, sizeof buf,
+                 "%s: fp32 dim=%d n=%zu shards=%d pair-symmetric(TI=%d,block=%d,itile=1024) seg_tiles=%d rows=%d "
+                 "units=%d grid=%d tiles=%lld cutoff=grid-prepass(plain|exact)%s + finish kernel",
+                 mode ? "step" : "forces", D, ctx->n, ctx->world, ti, block, seg, Q.n_rows, Q.total_units, grid,
+                 ctx->ntiles, cross ? " + reaction sums pushed to their owners over NVLink" : "");
+        ctx->plan = buf;
+    }
     return NB200_OK;
 }
 
@@ -662,6 +776,7 @@ int finish_timing(nb200_ctx* ctx) {
 }
 
 int init_common(nb200_ctx* ctx) {
+    ctx->acc_seq_issued.assign(ctx->shards.size(), 0ull);
     for (Shard& s : ctx->shards) {
         int rc = alloc_shard(ctx, s);
         if (rc) return rc;
@@ -1094,7 +1209,7 @@ int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out)
         CK(cudaStreamWaitEvent(s.compute, s.ev_gather[ctx->cur], 0));
         CK(cudaEventRecord(s.ev_start, s.compute));
         if (pl.flags) { if (int rcd = launch_detect(ctx, s, cutoff_r2, ctx->cur)) return rcd; }
-        if (use_symmetric(ctx)) {
+        if (use_symmetric(ctx, false)) {
             rc = launch_symmetric(ctx, s, 0, G, cutoff_r2, 0.0, ctx->cur);
         } else {
             Ranges all(0, (int)ctx->ntiles);
@@ -1181,7 +1296,9 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
                 rc = launch_detect(ctx, s, cutoff_r2, cur);
                 if (rc) return rc;
             }
-            if (split && use_nccl) {
+            if (use_symmetric(ctx, true)) {
+                rc = launch_symmetric(ctx, s, 1, G, cutoff_r2, dt, cur, hs_remote);
+            } else if (split && use_nccl) {
                 // two launches around the all-gather event: own sources, then the other shards'
                 Ranges own((int)s.tile_lo, (int)s.tile_hi);
                 trace_mark(ctx, s, s.compute, "A>", step);
@@ -1199,8 +1316,6 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
                 Handshake hs = hs_remote;
                 hs.lazy = true;
                 rc = launch_pass(ctx, s, pl, own_first, upi, 1, G, cutoff_r2, dt, cur, hs);
-            } else if (use_symmetric(ctx)) {
-                rc = launch_symmetric(ctx, s, 1, G, cutoff_r2, dt, cur);
             } else {
                 if (use_nccl) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
                 Ranges all(0, NT);

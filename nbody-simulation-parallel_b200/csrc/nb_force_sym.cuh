@@ -25,20 +25,57 @@
 #define NB_SYM_ROW 14                               // floats per lane row of the transpose scratch (12 used):
                                                     // 14 makes the STS.64 writes and the column reads bank-conflict free
 
+// One row of the work list: an i-tile of own targets against a run of source tiles.
+//   NB_ROW_SYM set:   every pair of the block is evaluated once and feeds both bodies
+//   NB_ROW_SYM clear: ordered pairs, targets only (the diagonal block holding the i-tile itself)
+struct NbSymRow {
+    int it;                      // own i-tile (1024 targets)
+    int t_begin, t_end;          // source tiles [t_begin, t_end), global tile indices
+    int flags;
+};
+#define NB_ROW_SYM 1
+
 struct NbSymParams {
-    const float* src;            // tile-planar sources (current step)
-    double* acc;                 // [3][tpad] FP64 accumulators of the own targets
+    const float* src;            // tile-planar sources (current step), all bodies
+    double* gacc;                // [3][gstride] FP64 accumulators indexed by GLOBAL body index
+    size_t gstride;
     unsigned* sched;             // [2] unit counter + exit counter (self-resetting)
-    const int* unit_prefix;      // [n_itiles + 1] first flat unit index of every i-tile
-    const unsigned char* suspect;
-    long long tgt_base;          // first own body (multiple of NB_SYM_ITILE)
-    int tpad;
-    int n_itiles;                // own i-tiles
-    int seg_tiles;               // source tiles per symmetric unit
-    int own_tile_begin;          // tgt_base / NB_TILE
-    int own_tile_end;            // one past the last own source tile
+    const NbSymRow* rows;        // [n_rows]
+    const int* row_prefix;       // [n_rows + 1] first flat unit index of every row
+    const unsigned char* suspect;   // [tpad] close-pair flags of the own targets
+    long long tgt_base;          // first own body (multiple of NB_TILE)
+    int own_count;               // bodies of this shard incl. tile padding; targets past it are inert
+    int n_rows;
+    int seg_tiles;               // source tiles per unit
     int total_units;
     float cutoff;                // scaled r^2 cut-off
+};
+
+// Reaction sums that belong to bodies of OTHER shards leave through nb_sym_push_kernel: the rows
+// of gacc that cover peer p's shard go to this rank's slot in p's receive buffer (plain coalesced
+// stores over NVLink peer memory), the local rows are cleared, and the last CTA publishes the
+// pass number on p's flag word.  The owner's nb_finish_kernel acquires the flags of all its senders.
+struct NbSymPush {
+    double* gacc;
+    size_t gstride;
+    int n_dst;
+    long long body_begin[4];     // first body of the destination shard
+    int count;                   // bodies per shard (incl. tile padding)
+    double* dst_slot[4];         // peer-mapped slot [3][count]
+    unsigned long long* dst_flag[4];   // peer-mapped flag word of (this rank -> peer)
+    unsigned long long seq;
+    unsigned* done;              // CTA completion counter (self-resetting)
+};
+
+struct NbSymFinish {
+    double* gacc;
+    size_t gstride;
+    int n_src;                   // senders whose slots must be added
+    const double* slot[4];       // local receive slots [3][count]
+    const unsigned long long* flag[4];   // local flag words of (sender -> this rank)
+    unsigned long long seq;      // 0 = nothing to wait for
+    int count;
+    unsigned* done;              // CTA completion counter for the step signal (self-resetting)
 };
 
 static inline size_t nb_sym_smem_bytes(int dim, int block) {
@@ -188,29 +225,29 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? 2 : 3) nb_force_sym_kern
     for (;;) {
         if (tid == 0) {
             const int u = (int)atomicAdd(&P.sched[0], 1u);
-            int it = -1, sg = 0;
+            int r = -1, sg = 0;
             if (u < P.total_units) {
-                int lo = 0, hi = P.n_itiles;            // largest it with unit_prefix[it] <= u
+                int lo = 0, hi = P.n_rows;              // largest row with row_prefix[row] <= u
                 while (hi - lo > 1) {
                     const int mid = (lo + hi) >> 1;
-                    if (P.unit_prefix[mid] <= u) lo = mid; else hi = mid;
+                    if (P.row_prefix[mid] <= u) lo = mid; else hi = mid;
                 }
-                it = lo;
-                sg = u - P.unit_prefix[lo];
+                r = lo;
+                sg = u - P.row_prefix[lo];
             }
-            s_unit[0] = it;
+            s_unit[0] = r;
             s_unit[1] = sg;
         }
         __syncthreads();
-        const int it = s_unit[0];
+        const int row = s_unit[0];
         const int sg = s_unit[1];
         __syncthreads();
-        if (it < 0) break;
-        // segment 0 = the diagonal unit (own four tiles, ordered pairs); segment s >= 1 = symmetric
-        const bool sym = sg > 0;
-        const int diag0 = P.own_tile_begin + it * (ITILE / NB_TILE);
-        const int ts = sym ? diag0 + ITILE / NB_TILE + (sg - 1) * P.seg_tiles : diag0;
-        const int te = sym ? min(ts + P.seg_tiles, P.own_tile_end) : min(diag0 + ITILE / NB_TILE, P.own_tile_end);
+        if (row < 0) break;
+        const NbSymRow R = P.rows[row];
+        const int it = R.it;
+        const bool sym = (R.flags & NB_ROW_SYM) != 0;
+        const int ts = R.t_begin + sg * P.seg_tiles;
+        const int te = min(ts + P.seg_tiles, R.t_end);
         const int ntl = te - ts;
 
         if (tid == 0) {
@@ -235,7 +272,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? 2 : 3) nb_force_sym_kern
             const float* tb = src + (size_t)(b / NB_TILE) * TILE_ELEMS + (b % NB_TILE);
 #pragma unroll
             for (int d = 0; d < 3; ++d) npos[t][d] = (d < D) ? -tb[d * NB_TILE] : 0.f;
-            mi[t] = tb[D * NB_TILE];
+            // the last i-tile of a shard may reach past the shard: those lanes must not react on anybody
+            mi[t] = (it * ITILE + tid + t * BLOCK < P.own_count) ? tb[D * NB_TILE] : 0.f;
             suspect |= P.suspect[it * ITILE + tid + t * BLOCK] != 0;
         }
         const bool warp_suspect = __any_sync(0xffffffffu, suspect) != 0;
@@ -283,13 +321,13 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? 2 : 3) nb_force_sym_kern
                 __syncthreads();
                 const float* bb = bout_all + (size_t)bbuf * NWARPS * (D * NB_TILE);
                 for (int j = tid; j < NB_TILE; j += BLOCK) {
-                    const long long lj = (long long)(ts + t) * NB_TILE + j - P.tgt_base;
+                    const size_t gj = (size_t)(ts + t) * NB_TILE + j;
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
                         float v = 0.f;
 #pragma unroll
                         for (int w = 0; w < NWARPS; ++w) v += bb[(size_t)w * (D * NB_TILE) + d * NB_TILE + j];
-                        atomicAdd(&P.acc[(size_t)d * P.tpad + lj], -(double)v);
+                        atomicAdd(&P.gacc[(size_t)d * P.gstride + gj], -(double)v);
                     }
                 }
                 bbuf ^= 1;
@@ -302,7 +340,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? 2 : 3) nb_force_sym_kern
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 const int li = it * ITILE + tid + t * BLOCK;
-                atomicAdd(&P.acc[(size_t)d * P.tpad + li], accd[t][d]);
+                if (li < P.own_count)
+                    atomicAdd(&P.gacc[(size_t)d * P.gstride + (size_t)P.tgt_base + li], accd[t][d]);
             }
     }
 
@@ -317,47 +356,99 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? 2 : 3) nb_force_sym_kern
     }
 }
 
+template <int D>
+__global__ void __launch_bounds__(256) nb_sym_push_kernel(const NbSymPush Q) {
+    const long long per = (long long)Q.count * D;
+    const long long total = per * Q.n_dst;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total;
+         k += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(k / per);
+        const long long r = k - (long long)p * per;
+        const int d = (int)(r / Q.count);
+        const long long j = r - (long long)d * Q.count;
+        double* g = &Q.gacc[(size_t)d * Q.gstride + (size_t)(Q.body_begin[p] + j)];
+        Q.dst_slot[p][(size_t)d * Q.count + j] = *g;
+        *g = 0.0;
+    }
+    __threadfence_system();                       // this thread's peer stores before the CTA's exit count
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned e = atomicAdd(Q.done, 1u);
+        if (e + 1u == gridDim.x) {
+            *Q.done = 0u;
+            __threadfence_system();
+            for (int p = 0; p < Q.n_dst; ++p) nb_st_release_sys(Q.dst_flag[p], Q.seq);
+        }
+    }
+}
+
 // Epilogue of a pass whose accumulators are complete only when the whole pass is (symmetric
-// pass): the same arithmetic as the fused epilogue of nb_force_kernel.
+// pass): the same arithmetic as the fused epilogue of nb_force_kernel, after adding the reaction
+// sums the other ranks pushed into this rank's receive slots.
 //   forces:  F_i = -(G m_i) S_i                                  methods.cpp:125-131
 //   step:    v += (F/m) dt ; x += v dt ; new source row           methods.cpp:436, :448
+// In step mode the new row also goes to every peer's next buffer (the fused exchange) and the last
+// CTA publishes the step number on the peers' step flags, exactly like nb_force_kernel's exit.
 template <int D, typename real>
-__global__ void __launch_bounds__(256) nb_finish_kernel(const NbForceParams P) {
+__global__ void __launch_bounds__(256) nb_finish_kernel(const NbForceParams P, const NbSymFinish F) {
     constexpr int NP = D + 1;
+    if (F.seq != 0ull && F.n_src > 0) {
+        if (threadIdx.x < F.n_src)
+            while (nb_ld_acquire_sys(F.flag[threadIdx.x]) < F.seq) __nanosleep(200);
+        __syncthreads();
+    }
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= P.tpad) return;
-    double S[3];
+    if (li < P.tpad) {
+        double S[3];
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-        double* ap = &P.acc[(size_t)d * P.tpad + li];
-        S[d] = *ap * P.acc_scale;
-        *ap = 0.0;                                   // self-clean for the next pass
+        for (int d = 0; d < D; ++d) {
+            double* ap = &F.gacc[(size_t)d * F.gstride + (size_t)P.tgt_base + li];
+            double v = *ap;
+            *ap = 0.0;                                   // self-clean for the next pass
+            if (li < F.count)
+                for (int k = 0; k < F.n_src; ++k) v += F.slot[k][(size_t)d * F.count + li];
+            S[d] = v * P.acc_scale;
+        }
+        if (li < P.n_local) {
+            const double m = P.mass[li];
+            const double gm = P.G * m;
+            double Fo[3];
+#pragma unroll
+            for (int d = 0; d < D; ++d) Fo[d] = -(gm * S[d]);
+            if (P.mode == 0) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) P.forces[(size_t)li * D + d] = Fo[d];
+            } else {
+                const long long b = P.tgt_base + li;
+                const size_t off0 = (size_t)(b / NB_TILE) * (NB_TILE * NP) + (b % NB_TILE);
+                real* nb = static_cast<real*>(P.src_next) + off0;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    double v = P.vel[(size_t)d * P.tpad + li];
+                    double x = P.pos[(size_t)d * P.tpad + li];
+                    v += (Fo[d] / m) * P.dt;
+                    x += v * P.dt;
+                    P.vel[(size_t)d * P.tpad + li] = v;
+                    P.pos[(size_t)d * P.tpad + li] = x;
+                    const real xs = (real)(x * P.pos_scale);
+                    nb[d * NB_TILE] = xs;
+                    for (int pr = 0; pr < P.n_peers; ++pr)
+                        static_cast<real*>(P.peer_next[pr])[off0 + (size_t)d * NB_TILE] = xs;
+                }
+            }
+        }
     }
-    if (li >= P.n_local) return;
-    const double m = P.mass[li];
-    const double gm = P.G * m;
-    double F[3];
-#pragma unroll
-    for (int d = 0; d < D; ++d) F[d] = -(gm * S[d]);
-    if (P.mode == 0) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) P.forces[(size_t)li * D + d] = F[d];
-        return;
-    }
-    const long long b = P.tgt_base + li;
-    const size_t off0 = (size_t)(b / NB_TILE) * (NB_TILE * NP) + (b % NB_TILE);
-    real* nb = static_cast<real*>(P.src_next) + off0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-        double v = P.vel[(size_t)d * P.tpad + li];
-        double x = P.pos[(size_t)d * P.tpad + li];
-        v += (F[d] / m) * P.dt;
-        x += v * P.dt;
-        P.vel[(size_t)d * P.tpad + li] = v;
-        P.pos[(size_t)d * P.tpad + li] = x;
-        const real xs = (real)(x * P.pos_scale);
-        nb[d * NB_TILE] = xs;
-        for (int pr = 0; pr < P.n_peers; ++pr)
-            static_cast<real*>(P.peer_next[pr])[off0 + (size_t)d * NB_TILE] = xs;
+    if (P.signal_step != 0ull && P.n_peers > 0) {
+        __threadfence_system();                   // remote rows before the exit count
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned e = atomicAdd(F.done, 1u);
+            if (e + 1u == gridDim.x) {
+                *F.done = 0u;
+                __threadfence_system();
+                for (int pr = 0; pr < P.n_peers; ++pr)
+                    nb_st_release_sys(P.peer_flags[pr] + P.my_rank, P.signal_step);
+            }
+        }
     }
 }

@@ -351,11 +351,25 @@ def test_single_process_multi_gpu_matches_one_gpu(pkg, ngpus, prec):
                                                options={"exchange": exchange, "overlap": overlap})
             err = np.abs(ag - a1).max() / np.abs(a1).max()
             assert err <= 1e-10, f"exchange={exchange} overlap={overlap}: {err:.3e}"
+    if prec == 32:
+        # cross-rank pair-symmetric pass: every block of pairs evaluated by ONE of its two ranks, the
+        # reaction sums pushed to the other over NVLink (needs the pre-pass; FP32 sums reorder)
+        for ti in (4, 8):
+            ag = pkg.brute_force_cuda_simulate(b, 1e-3, 10, prec, ngpus=ngpus,
+                                               options={"detect": 1, "symmetric": 1, "sym_ti": ti, "seg_tiles": 3})
+            err = np.abs(ag - a1).max() / np.abs(a1).max()
+            assert err <= 1e-6, f"cross-rank symmetric TI={ti}: {err:.3e}"
+        # ragged shards: the last i-tile of every shard reaches into the next shard's bodies
+        br = pkg.generators.plummer(23000 + 777 * ngpus, seed=6)
+        r1 = pkg.brute_force_cuda_simulate(br, 1e-3, 6, prec, options={"detect": 1, "symmetric": 0})
+        rg = pkg.brute_force_cuda_simulate(br, 1e-3, 6, prec, ngpus=ngpus, options={"detect": 1, "symmetric": 1})
+        err = np.abs(rg - r1).max() / np.abs(r1).max()
+        assert err <= 1e-6, f"cross-rank symmetric, ragged shards: {err:.3e}"
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-@pytest.mark.parametrize("overlap", [1, 0])
-def test_one_process_per_gpu_torchrun(exchange, overlap):
+@pytest.mark.parametrize("exchange,overlap,extra", [("p2p", 1, []), ("p2p", 0, []), ("nccl", 1, []), ("nccl", 0, []),
+                                                    ("p2p", 1, ["--detect", "1", "--precision", "32"])])
+def test_one_process_per_gpu_torchrun(exchange, overlap, extra):
     """The torchrun flavour (one rank per GPU, CUDA IPC handles all-gathered over torch.distributed)."""
     import os
     import subprocess
@@ -363,10 +377,10 @@ def test_one_process_per_gpu_torchrun(exchange, overlap):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    port = 29600 + (0 if exchange == "p2p" else 2) + overlap
+    port = 29600 + (0 if exchange == "p2p" else 2) + overlap + (4 if extra else 0)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
-                        os.path.join(root, "tools", "mp_check.py"), "--exchange", exchange, "--overlap", str(overlap)],
+                        os.path.join(root, "tools", "mp_check.py"), "--exchange", exchange, "--overlap", str(overlap)] + extra,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MP_CHECK" in r.stdout and " OK " in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 

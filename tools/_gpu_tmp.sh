@@ -1,2 +1,1 @@
-for n in 262144 1048576; do for ti in 4 8; do python tools/run_case.py --n $n --steps 2 --warmup 1 --opt symmetric=1 --opt sym_ti=$ti; done; done
-python tools/run_case.py --n 131072 --dim 2 --steps 2 --warmup 1 --opt symmetric=1 --opt sym_ti=8
+timeout 600 python -m pytest tests -m gpu -x -q -k "multi_gpu or torchrun or symmetric" 2>&1 | tail -5
