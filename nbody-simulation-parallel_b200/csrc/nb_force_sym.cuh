@@ -270,10 +270,13 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? 2 : 3) nb_force_sym_kern
             const long long b = P.tgt_base + (long long)it * ITILE + tid + t * BLOCK;
             own_tile[t] = (int)(b / NB_TILE);
             const float* tb = src + (size_t)(b / NB_TILE) * TILE_ELEMS + (b % NB_TILE);
+            // The last i-tile of a shard may reach past the shard's bodies (into the next shard's, which
+            // also appear as SOURCES of the cross-shard rows: a self pair outside the exact pass).  Such
+            // lanes are made inert: parked far away (1/r^4 underflows to 0) with zero mass, nothing stored.
+            const bool live = it * ITILE + tid + t * BLOCK < P.own_count;
 #pragma unroll
-            for (int d = 0; d < 3; ++d) npos[t][d] = (d < D) ? -tb[d * NB_TILE] : 0.f;
-            // the last i-tile of a shard may reach past the shard: those lanes must not react on anybody
-            mi[t] = (it * ITILE + tid + t * BLOCK < P.own_count) ? tb[D * NB_TILE] : 0.f;
+            for (int d = 0; d < 3; ++d) npos[t][d] = (d < D) ? (live ? -tb[d * NB_TILE] : -1.0e15f) : 0.f;
+            mi[t] = live ? tb[D * NB_TILE] : 0.f;
             suspect |= P.suspect[it * ITILE + tid + t * BLOCK] != 0;
         }
         const bool warp_suspect = __any_sync(0xffffffffu, suspect) != 0;

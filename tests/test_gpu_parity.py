@@ -360,7 +360,7 @@ def test_single_process_multi_gpu_matches_one_gpu(pkg, ngpus, prec):
             err = np.abs(ag - a1).max() / np.abs(a1).max()
             assert err <= 1e-6, f"cross-rank symmetric TI={ti}: {err:.3e}"
         # ragged shards: the last i-tile of every shard reaches into the next shard's bodies
-        br = pkg.generators.plummer(23000 + 777 * ngpus, seed=6)
+        br = pkg.generators.plummer(25000 + 1000 * ngpus, seed=6)     # 53 / 29 / 17 tiles per shard
         r1 = pkg.brute_force_cuda_simulate(br, 1e-3, 6, prec, options={"detect": 1, "symmetric": 0})
         rg = pkg.brute_force_cuda_simulate(br, 1e-3, 6, prec, ngpus=ngpus, options={"detect": 1, "symmetric": 1})
         err = np.abs(rg - r1).max() / np.abs(r1).max()
@@ -415,10 +415,11 @@ def test_padded_and_packed_records_round_trip(pkg, oracle, dim, prec):
         packed = np.zeros((n, w))
         ctx.download(packed)
         assert np.array_equal(packed[:, 2 * dim], b[:, 2 * dim])   # packed records: uploaded mass comes back
-    tol = 1e-12 if prec == 64 else 2e-6
     scale = np.abs(want[:, :2 * dim]).max()
-    assert np.abs(out[:, :2 * dim] - want[:, :2 * dim]).max() <= tol * scale
-    assert np.array_equal(out[:, :2 * dim], packed[:, :2 * dim])
+    if prec == 64:      # (FP32 accuracy is judged by the kappa-aware force tests, not here)
+        assert np.abs(out[:, :2 * dim] - want[:, :2 * dim]).max() <= 1e-12 * scale
+    # two runs of the same steps: FP64 atomics may add the unit partial sums in another order
+    assert np.abs(out[:, :2 * dim] - packed[:, :2 * dim]).max() <= (1e-13 if prec == 64 else 1e-6) * scale
 
 
 def test_fp32_scales_come_from_the_device_side_bounds(pkg, oracle):
