@@ -143,6 +143,11 @@ long long nb200_launch_count(const nb200_ctx* ctx);
  *                 1 with the fused exchange, 0 with NCCL)
  *   "exchange"    1 = fused NVLink peer stores from the epilogue (default when attached), 0 = ncclAllGather
  *   "trace"       1 = append a CUDA-event timeline of shard 0 to nb200_plan() after nb200_step
+ *   "symmetric"   1/0 = pair-symmetric pass on/off (default on whenever the close-pair pre-pass runs):
+ *                 every unordered pair is evaluated once and feeds both bodies, like the j > i loop of
+ *                 brute_force_seq_n_body (methods.cpp:18-39); across ranks the reaction sums are pushed
+ *                 to their owner over NVLink (needs the fused exchange)
+ *   "sym_ti"      4 | 8 targets per thread in the FP32 pair-symmetric kernel (0 = auto)
  * Returns NB200_EINVAL for an unknown key. */
 int nb200_set_option(nb200_ctx* ctx, const char* key, long value);
 

@@ -203,7 +203,7 @@ struct nb200_ctx {
     std::vector<unsigned long long> acc_seq_issued;   // per driven shard: pair-symmetric passes with a reaction exchange so far
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 4;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
@@ -243,6 +243,14 @@ int fail(nb200_ctx* c, int code, const char* fmt, ...) {
 
 constexpr int kMaxItile = 1024;
 
+typedef void (*SymKernel)(const NbSymParams);
+// pair-symmetric kernels: FP32 in two register-block shapes (4 targets x 256 threads, 8 x 128), FP64 in one
+SymKernel pick_sym_kernel(int dim, bool f64, int ti) {
+    if (f64) return dim == 3 ? nb_force_sym_kernel<3, true, 4, 256> : nb_force_sym_kernel<2, true, 4, 256>;
+    if (dim == 3) return ti == 8 ? nb_force_sym_kernel<3, false, 8, 128> : nb_force_sym_kernel<3, false, 4, 256>;
+    return ti == 8 ? nb_force_sym_kernel<2, false, 8, 128> : nb_force_sym_kernel<2, false, 4, 256>;
+}
+
 int alloc_shard(nb200_ctx* ctx, Shard& s) {
     const int D = ctx->dim;
     const size_t rs = ctx->f64 ? 8 : 4;
@@ -281,7 +289,7 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
         CK(cudaMalloc(&s.grid_counts, (size_t)cap * sizeof(unsigned)));
         CK(cudaMalloc(&s.suspect, tp));
         CK(cudaMemset(s.suspect, 1, tp));
-        if (!ctx->f64) {
+        {
             // rows: per own i-tile one ordered + one triangular row, plus one row per cross-shard block
             s.sym_rows_cap = (int)(tp / NB_SYM_ITILE + 1) * (2 + kSymMaxSlots);
             CK(cudaMalloc(&s.sym_rows, (size_t)s.sym_rows_cap * sizeof(NbSymRow)));
@@ -295,7 +303,7 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
     {
         // flag words (step, epoch, reaction-sum pass: one per writer rank each) and, behind them in the
         // SAME allocation (one IPC handle), the receive slots of the pair-symmetric pass
-        const size_t slots = ctx->f64 ? 0 : (size_t)kSymMaxSlots * 3 * (size_t)ctx->tiles_per_shard * NB_TILE * sizeof(double);
+        const size_t slots = (size_t)kSymMaxSlots * 3 * (size_t)ctx->tiles_per_shard * NB_TILE * sizeof(double);
         CK(cudaMalloc(&s.flags, kFlagsBytes + slots));
         CK(cudaMemset(s.flags, 0, kFlagsBytes));
     }
@@ -307,12 +315,9 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
             CK(cudaFuncSetAttribute((const void*)pick_kernel(D, ctx->f64, v, fl != 0),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem_bytes(D, ctx->f64)));
-    if (!ctx->f64) {
-        const void* ks[2] = {D == 3 ? (const void*)nb_force_sym_kernel<3, 4, 256> : (const void*)nb_force_sym_kernel<2, 4, 256>,
-                             D == 3 ? (const void*)nb_force_sym_kernel<3, 8, 128> : (const void*)nb_force_sym_kernel<2, 8, 128>};
-        CK(cudaFuncSetAttribute(ks[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nb_sym_smem_bytes(D, 256)));
-        CK(cudaFuncSetAttribute(ks[1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nb_sym_smem_bytes(D, 128)));
-    }
+    for (int ti = 4; ti <= (ctx->f64 ? 4 : 8); ti += 4)
+        CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, ti), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)nb_sym_smem_bytes(D, NB_SYM_ITILE / ti, ctx->f64)));
     return NB200_OK;
 }
 
@@ -578,7 +583,7 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
 // off = 1 .. floor((G-1)/2) and, for even G, half of the block against the opposite rank; the
 // reaction sums on the other rank's bodies are pushed into that rank's receive slots.
 bool use_symmetric(const nb200_ctx* ctx, bool stepping) {
-    if (ctx->f64 || !use_detect(ctx) || ctx->opt_symmetric == 0) return false;
+    if (!use_detect(ctx) || ctx->opt_symmetric == 0) return false;
     if (ctx->world == 1) return true;
     // cross-rank flavour: only inside nb200_step (nb200_forces stays a rank-local call)
     return stepping && !ctx->detached && ctx->p2p_ready && ctx->exchange == 1 && ctx->world <= kMaxWorldP2P;
@@ -648,7 +653,7 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     if (int rc = build_sym_rows(ctx, s, seg, cross)) return rc;
     NbSymParams Q;
     memset(&Q, 0, sizeof Q);
-    Q.src = static_cast<const float*>(s.src[cur]);
+    Q.src = s.src[cur];
     Q.gacc = s.gacc;
     Q.gstride = (size_t)ctx->nalloc;
     Q.sched = s.sched;
@@ -660,14 +665,14 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     Q.n_rows = (int)s.sym_rows_host.size();
     Q.seg_tiles = seg;
     Q.total_units = s.sym_prefix_host.back();
-    Q.cutoff = (float)(cutoff * ctx->pos_scale * ctx->pos_scale);
+    Q.cutoff = cutoff * ctx->pos_scale * ctx->pos_scale;
     // two register-block shapes of the same 1024-target i-tile: 4 targets x 256 threads, 8 x 128
-    const int ti = ctx->opt_sym_ti == 8 ? 8 : 4;
+    // auto: the 2D chain is shorter, so the per-iteration reduction weighs more: 8 targets per thread there
+    const int want_ti = ctx->opt_sym_ti ? ctx->opt_sym_ti : (D == 2 ? 8 : 4);
+    const int ti = (!ctx->f64 && want_ti == 8) ? 8 : 4;
     const int block = NB_SYM_ITILE / ti;
-    typedef void (*SymKernel)(const NbSymParams);
-    const SymKernel kfn = D == 3 ? (ti == 8 ? nb_force_sym_kernel<3, 8, 128> : nb_force_sym_kernel<3, 4, 256>)
-                                 : (ti == 8 ? nb_force_sym_kernel<2, 8, 128> : nb_force_sym_kernel<2, 4, 256>);
-    const size_t smem = nb_sym_smem_bytes(D, block);
+    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, ti);
+    const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64);
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kfn, block, smem));
     const int grid = std::min(std::max(1, nb) * s.sms, Q.total_units);
@@ -715,16 +720,21 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     }
     NbForceParams P = base_params(ctx, s, mode, G, cutoff, dt, cur, hs);
     const int fb = (s.tpad + 255) / 256;
-    if (D == 3) nb_finish_kernel<3, float><<<fb, 256, 0, s.compute>>>(P, F);
-    else nb_finish_kernel<2, float><<<fb, 256, 0, s.compute>>>(P, F);
+    if (ctx->f64) {
+        if (D == 3) nb_finish_kernel<3, double><<<fb, 256, 0, s.compute>>>(P, F);
+        else nb_finish_kernel<2, double><<<fb, 256, 0, s.compute>>>(P, F);
+    } else {
+        if (D == 3) nb_finish_kernel<3, float><<<fb, 256, 0, s.compute>>>(P, F);
+        else nb_finish_kernel<2, float><<<fb, 256, 0, s.compute>>>(P, F);
+    }
     CK(cudaGetLastError());
     ctx->launches++;
     if (&s == &ctx->shards[0]) {
         char buf[320];
         snprintf(buf, sizeof buf,
-                 "%s: fp32 dim=%d n=%zu shards=%d pair-symmetric(TI=%d,block=%d,itile=1024) seg_tiles=%d rows=%d "
+                 "%s: fp%d dim=%d n=%zu shards=%d pair-symmetric(TI=%d,block=%d,itile=1024) seg_tiles=%d rows=%d "
                  "units=%d grid=%d tiles=%lld cutoff=grid-prepass(plain|exact)%s + finish kernel",
-                 mode ? "step" : "forces", D, ctx->n, ctx->world, ti, block, seg, Q.n_rows, Q.total_units, grid,
+                 mode ? "step" : "forces", ctx->f64 ? 64 : 32, D, ctx->n, ctx->world, ti, block, seg, Q.n_rows, Q.total_units, grid,
                  ctx->ntiles, cross ? " + reaction sums pushed to their owners over NVLink" : "");
         ctx->plan = buf;
     }
@@ -1092,7 +1102,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "trace")) ctx->opt_trace = value != 0;
     else if (!strcmp(key, "detect")) ctx->opt_detect = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "symmetric")) ctx->opt_symmetric = value < 0 ? -1 : (value != 0);
-    else if (!strcmp(key, "sym_ti")) ctx->opt_sym_ti = value == 8 ? 8 : 4;
+    else if (!strcmp(key, "sym_ti")) ctx->opt_sym_ti = value == 8 ? 8 : value == 4 ? 4 : 0;
     else if (!strcmp(key, "exchange")) {
         if (value == 1 && !ctx->p2p_ready) return fail(ctx, NB200_ESTATE, "peer-store exchange is not attached");
         if (value == 0 && ctx->rank_mode && ctx->world > 1 && !ctx->detached && !ctx->shards[0].comm_nccl)

@@ -36,7 +36,7 @@ struct NbSymRow {
 #define NB_ROW_SYM 1
 
 struct NbSymParams {
-    const float* src;            // tile-planar sources (current step), all bodies
+    const void* src;             // tile-planar sources (current step), all bodies (float or double)
     double* gacc;                // [3][gstride] FP64 accumulators indexed by GLOBAL body index
     size_t gstride;
     unsigned* sched;             // [2] unit counter + exit counter (self-resetting)
@@ -48,7 +48,7 @@ struct NbSymParams {
     int n_rows;
     int seg_tiles;               // source tiles per unit
     int total_units;
-    float cutoff;                // scaled r^2 cut-off
+    double cutoff;               // r^2 cut-off in source units
 };
 
 // Reaction sums that belong to bodies of OTHER shards leave through nb_sym_push_kernel: the rows
@@ -78,11 +78,12 @@ struct NbSymFinish {
     unsigned* done;              // CTA completion counter for the step signal (self-resetting)
 };
 
-static inline size_t nb_sym_smem_bytes(int dim, int block) {
-    const size_t ring = (size_t)NB_STAGES * NB_TILE * (dim + 1) * sizeof(float);
+static inline size_t nb_sym_smem_bytes(int dim, int block, bool f64) {
+    const size_t rs = f64 ? 8 : 4;
+    const size_t ring = (size_t)NB_STAGES * NB_TILE * (dim + 1) * rs;
     const size_t bars = 2 * NB_STAGES * sizeof(uint64_t) + 16;
     const size_t scr = (size_t)(block / 32) * 2 * 32 * NB_SYM_ROW * sizeof(float);
-    const size_t bout = (size_t)2 * (block / 32) * dim * NB_TILE * sizeof(float);
+    const size_t bout = (size_t)2 * (block / 32) * dim * NB_TILE * rs;
     return ring + bars + scr + bout;
 }
 
@@ -188,26 +189,112 @@ __device__ __forceinline__ void nb_tile_f32_sym(const float* __restrict__ stage,
     __syncwarp();
 }
 
-template <int D, int TI, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? 2 : 3) nb_force_sym_kernel(const NbSymParams P) {
+// FP64 flavour: scalar DFMA chains, two sources per iteration, sums kept in FP64 end to end.
+// Per unordered pair 18 DP operations (3 DADD, DMUL + 2 DFMA, 3 DFMA of the reciprocal, DMUL for
+// 1/r^4, 2 DMUL for the two masses, 2 x 3 DFMA) instead of 2 x 14.  The lane rows of the transpose hold
+// 6 doubles (stride 7): reducer lane (o, part) adds the rows 4k + part of output o = component*2 + source.
+template <int D, int TI, bool EXACT>
+__device__ __forceinline__ void nb_tile_f64_sym(const double* __restrict__ stage, double cutoff,
+                                                const double (&pos)[TI][3], const double (&mi)[TI],
+                                                double (&accd)[TI][3], double* __restrict__ scr,
+                                                double* __restrict__ wout, int lane) {
+    constexpr int ROWD = NB_SYM_ROW / 2;                      // doubles per lane row
+    const double2* sx = reinterpret_cast<const double2*>(stage);
+    const double2* sy = sx + NB_TILE / 2;
+    const double2* sz = sy + NB_TILE / 2;                     // D == 3 only
+    const double2* sm = sx + D * (NB_TILE / 2);
+    const int o = lane >> 2, part = lane & 3;
+    const bool reducer = o < 2 * D;
+    const int oc = reducer ? o : 0;
+    const double* rbase = scr + part * ROWD + oc;
+    double* wbase = wout + (oc >> 1) * NB_TILE + (oc & 1);
+    const bool writer = reducer && part == 0;
+    auto reduce_store = [&](int q_done, int buf) {
+        const double* rb = rbase + buf * (32 * ROWD);
+        double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            v0 += rb[(4 * k) * ROWD];
+            v1 += rb[(4 * k + 4) * ROWD];
+        }
+        double v = v0 + v1;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (writer && q_done >= 0) wbase[q_done * 2] = v;
+    };
+
+#pragma unroll 1
+    for (int q = 0; q < NB_TILE / 2; ++q) {
+        const double2 X = sx[q], Y = sy[q], M = sm[q];
+        double2 Z = make_double2(0.0, 0.0);
+        if (D == 3) Z = sz[q];
+        double b[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double xs = h ? X.y : X.x, ys = h ? Y.y : Y.x, zs = h ? Z.y : Z.x;
+            const double ms = h ? M.y : M.x;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) b[h][d] = 0.0;
+#pragma unroll
+            for (int t = 0; t < TI; ++t) {
+                const double dx = xs - pos[t][0];
+                const double dy = ys - pos[t][1];
+                double r2 = dx * dx;
+                r2 = fma(dy, dy, r2);
+                double dz = 0.0;
+                if (D == 3) {
+                    dz = zs - pos[t][2];
+                    r2 = fma(dz, dz, r2);
+                }
+                double inv = nb_rcp_f64(r2);
+                if (EXACT) inv = (r2 >= cutoff) ? inv : 0.0;  // drop (also kills the NaN of r2 = 0)
+                const double w = inv * inv;
+                const double s = w * ms;
+                const double u = w * mi[t];
+                accd[t][0] = fma(s, dx, accd[t][0]);
+                b[h][0] = fma(u, dx, b[h][0]);
+                accd[t][1] = fma(s, dy, accd[t][1]);
+                b[h][1] = fma(u, dy, b[h][1]);
+                if (D == 3) {
+                    accd[t][2] = fma(s, dz, accd[t][2]);
+                    b[h][2] = fma(u, dz, b[h][2]);
+                }
+            }
+        }
+        reduce_store(q - 1, (q + 1) & 1);   // q = 0: nothing stored
+        double* row = scr + (q & 1) * (32 * ROWD) + lane * ROWD;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            row[2 * d] = b[0][d];
+            row[2 * d + 1] = b[1][d];
+        }
+        __syncwarp();
+    }
+    reduce_store(NB_TILE / 2 - 1, (NB_TILE / 2 - 1) & 1);
+    __syncwarp();
+}
+
+template <int D, bool F64, int TI, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, F64 ? 1 : (BLOCK == 256 ? 2 : 3)) nb_force_sym_kernel(const NbSymParams P) {
+    using real = typename NbReal<F64>::type;
     constexpr int NP = D + 1;
     constexpr int ITILE = NB_SYM_ITILE;
     static_assert(TI * BLOCK == ITILE, "i-tile is 1024 targets");
     constexpr int TILE_ELEMS = NB_TILE * NP;
-    constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(float);
+    constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(real);
     constexpr int NWARPS = BLOCK / 32;
 
     extern __shared__ __align__(128) unsigned char nb_smem[];
-    float* ring = reinterpret_cast<float*>(nb_smem);
+    real* ring = reinterpret_cast<real*>(nb_smem);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(nb_smem + (size_t)NB_STAGES * TILE_BYTES);
     uint64_t* empty_bar = full_bar + NB_STAGES;
     int* s_unit = reinterpret_cast<int*>(empty_bar + NB_STAGES);   // [0] i-tile (or -1), [1] segment
     float* scr_all = reinterpret_cast<float*>(s_unit + 4);
-    float* bout_all = scr_all + (size_t)NWARPS * 2 * 32 * NB_SYM_ROW;   // [2][NWARPS][D][NB_TILE]
+    real* bout_all = reinterpret_cast<real*>(scr_all + (size_t)NWARPS * 2 * 32 * NB_SYM_ROW);   // [2][NWARPS][D][NB_TILE]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const float* __restrict__ src = P.src;
+    const real* __restrict__ src = static_cast<const real*>(P.src);
     float* scr = scr_all + (size_t)warp * 2 * 32 * NB_SYM_ROW;
 
     if (tid == 0) {
@@ -262,21 +349,25 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? 2 : 3) nb_force_sym_kern
             }
         }
 
-        float npos[TI][3], mi[TI];
+        real tq[TI][3], mi[TI];          // FP32: NEGATED target coordinates (operand of the packed add); FP64: plain
         int own_tile[TI];
         bool suspect = false;
 #pragma unroll
         for (int t = 0; t < TI; ++t) {
             const long long b = P.tgt_base + (long long)it * ITILE + tid + t * BLOCK;
             own_tile[t] = (int)(b / NB_TILE);
-            const float* tb = src + (size_t)(b / NB_TILE) * TILE_ELEMS + (b % NB_TILE);
+            const real* tb = src + (size_t)(b / NB_TILE) * TILE_ELEMS + (b % NB_TILE);
             // The last i-tile of a shard may reach past the shard's bodies (into the next shard's, which
             // also appear as SOURCES of the cross-shard rows: a self pair outside the exact pass).  Such
             // lanes are made inert: parked far away (1/r^4 underflows to 0) with zero mass, nothing stored.
             const bool live = it * ITILE + tid + t * BLOCK < P.own_count;
+            const real park = F64 ? real(1.0e150) : real(1.0e15f);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) npos[t][d] = (d < D) ? (live ? -tb[d * NB_TILE] : -1.0e15f) : 0.f;
-            mi[t] = live ? tb[D * NB_TILE] : 0.f;
+            for (int d = 0; d < 3; ++d) {
+                const real x = (d < D) ? (live ? tb[d * NB_TILE] : park) : real(0);
+                tq[t][d] = F64 ? x : -x;
+            }
+            mi[t] = live ? tb[D * NB_TILE] : real(0);
             suspect |= P.suspect[it * ITILE + tid + t * BLOCK] != 0;
         }
         const bool warp_suspect = __any_sync(0xffffffffu, suspect) != 0;
@@ -299,35 +390,57 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? 2 : 3) nb_force_sym_kern
             const unsigned k = kt + t;
             const int slot = k % NB_STAGES;
             nb_mbar_wait(&full_bar[slot], (k / NB_STAGES) & 1u);
-            const float* stage = ring + (size_t)slot * TILE_ELEMS;
-            float2 a[TI][3];
-            if (sym) {
-                float* wout = bout_all + ((size_t)bbuf * NWARPS + warp) * (D * NB_TILE);
-                if (warp_suspect) nb_tile_f32_sym<D, TI, NB_EXACT>(stage, P.cutoff, npos, mi, a, scr, wout, lane);
-                else nb_tile_f32_sym<D, TI, NB_PLAIN>(stage, P.cutoff, npos, mi, a, scr, wout, lane);
-            } else {
-                bool exact_tile = warp_suspect;
+            const real* stage = ring + (size_t)slot * TILE_ELEMS;
+            real* wout = bout_all + ((size_t)bbuf * NWARPS + warp) * (D * NB_TILE);
+            bool exact_tile = warp_suspect;
+            if (!sym) {
 #pragma unroll
                 for (int tt = 0; tt < TI; ++tt) exact_tile |= (ts + t == own_tile[tt]);
-                if (exact_tile) nb_tile_f32<D, TI, 1, NB_EXACT, 1>(stage, 0, P.cutoff, npos, a);
-                else nb_tile_f32<D, TI, 1, NB_PLAIN, 1>(stage, 0, P.cutoff, npos, a);
             }
+            if constexpr (F64) {
+                const double* dstage = reinterpret_cast<const double*>(stage);
+                const double(&pos)[TI][3] = reinterpret_cast<const double(&)[TI][3]>(tq);
+                const double(&mid)[TI] = reinterpret_cast<const double(&)[TI]>(mi);
+                double* dscr = reinterpret_cast<double*>(scr);
+                double* dwout = reinterpret_cast<double*>(wout);
+                if (sym) {
+                    if (exact_tile) nb_tile_f64_sym<D, TI, true>(dstage, P.cutoff, pos, mid, accd, dscr, dwout, lane);
+                    else nb_tile_f64_sym<D, TI, false>(dstage, P.cutoff, pos, mid, accd, dscr, dwout, lane);
+                } else {
+                    if (exact_tile) nb_tile_f64<D, TI, 1, true>(dstage, 0, P.cutoff, pos, accd);
+                    else nb_tile_f64<D, TI, 1, false>(dstage, 0, P.cutoff, pos, accd);
+                }
+            } else {
+                const float* fstage = reinterpret_cast<const float*>(stage);
+                const float(&npos)[TI][3] = reinterpret_cast<const float(&)[TI][3]>(tq);
+                const float(&mif)[TI] = reinterpret_cast<const float(&)[TI]>(mi);
+                const float cutoff_f = (float)P.cutoff;
+                float2 a[TI][3];
+                if (sym) {
+                    float* fwout = reinterpret_cast<float*>(wout);
+                    if (exact_tile) nb_tile_f32_sym<D, TI, NB_EXACT>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
+                    else nb_tile_f32_sym<D, TI, NB_PLAIN>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
+                } else {
+                    if (exact_tile) nb_tile_f32<D, TI, 1, NB_EXACT, 1>(fstage, 0, cutoff_f, npos, a);
+                    else nb_tile_f32<D, TI, 1, NB_PLAIN, 1>(fstage, 0, cutoff_f, npos, a);
+                }
 #pragma unroll
-            for (int tt = 0; tt < TI; ++tt)
+                for (int tt = 0; tt < TI; ++tt)
 #pragma unroll
-                for (int d = 0; d < D; ++d) accd[tt][d] += (double)(a[tt][d].x + a[tt][d].y);
+                    for (int d = 0; d < D; ++d) accd[tt][d] += (double)(a[tt][d].x + a[tt][d].y);
+            }
             __syncwarp();
             if (lane == 0) nb_mbar_arrive(&empty_bar[slot]);
             if (sym) {
                 // CTA-wide sum of the eight warps' tile buffers, one FP64 atomic per (source, component);
                 // the reaction on source j is MINUS sum_i (m_i / r^4) d_ij
                 __syncthreads();
-                const float* bb = bout_all + (size_t)bbuf * NWARPS * (D * NB_TILE);
+                const real* bb = bout_all + (size_t)bbuf * NWARPS * (D * NB_TILE);
                 for (int j = tid; j < NB_TILE; j += BLOCK) {
                     const size_t gj = (size_t)(ts + t) * NB_TILE + j;
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
-                        float v = 0.f;
+                        real v = real(0);
 #pragma unroll
                         for (int w = 0; w < NWARPS; ++w) v += bb[(size_t)w * (D * NB_TILE) + d * NB_TILE + j];
                         atomicAdd(&P.gacc[(size_t)d * P.gstride + gj], -(double)v);

@@ -351,20 +351,20 @@ def test_single_process_multi_gpu_matches_one_gpu(pkg, ngpus, prec):
                                                options={"exchange": exchange, "overlap": overlap})
             err = np.abs(ag - a1).max() / np.abs(a1).max()
             assert err <= 1e-10, f"exchange={exchange} overlap={overlap}: {err:.3e}"
-    if prec == 32:
-        # cross-rank pair-symmetric pass: every block of pairs evaluated by ONE of its two ranks, the
-        # reaction sums pushed to the other over NVLink (needs the pre-pass; FP32 sums reorder)
-        for ti in (4, 8):
-            ag = pkg.brute_force_cuda_simulate(b, 1e-3, 10, prec, ngpus=ngpus,
-                                               options={"detect": 1, "symmetric": 1, "sym_ti": ti, "seg_tiles": 3})
-            err = np.abs(ag - a1).max() / np.abs(a1).max()
-            assert err <= 1e-6, f"cross-rank symmetric TI={ti}: {err:.3e}"
-        # ragged shards: the last i-tile of every shard reaches into the next shard's bodies
-        br = pkg.generators.plummer(25000 + 1000 * ngpus, seed=6)     # 53 / 29 / 17 tiles per shard
-        r1 = pkg.brute_force_cuda_simulate(br, 1e-3, 6, prec, options={"detect": 1, "symmetric": 0})
-        rg = pkg.brute_force_cuda_simulate(br, 1e-3, 6, prec, ngpus=ngpus, options={"detect": 1, "symmetric": 1})
-        err = np.abs(rg - r1).max() / np.abs(r1).max()
-        assert err <= 1e-6, f"cross-rank symmetric, ragged shards: {err:.3e}"
+    # cross-rank pair-symmetric pass: every block of pairs evaluated by ONE of its two ranks, the
+    # reaction sums pushed to the other over NVLink (needs the pre-pass; FP32 sums reorder)
+    tol = 1e-6 if prec == 32 else 1e-10
+    for ti in ((4, 8) if prec == 32 else (4,)):
+        ag = pkg.brute_force_cuda_simulate(b, 1e-3, 10, prec, ngpus=ngpus,
+                                           options={"detect": 1, "symmetric": 1, "sym_ti": ti, "seg_tiles": 3})
+        err = np.abs(ag - a1).max() / np.abs(a1).max()
+        assert err <= tol, f"cross-rank symmetric TI={ti}: {err:.3e}"
+    # ragged shards: the last i-tile of every shard reaches into the next shard's bodies
+    br = pkg.generators.plummer(25000 + 1000 * ngpus, seed=6)     # 53 / 29 / 17 tiles per shard
+    r1 = pkg.brute_force_cuda_simulate(br, 1e-3, 6, prec, options={"detect": 1, "symmetric": 0})
+    rg = pkg.brute_force_cuda_simulate(br, 1e-3, 6, prec, ngpus=ngpus, options={"detect": 1, "symmetric": 1})
+    err = np.abs(rg - r1).max() / np.abs(r1).max()
+    assert err <= tol, f"cross-rank symmetric, ragged shards: {err:.3e}"
 
 
 @pytest.mark.parametrize("exchange,overlap,extra", [("p2p", 1, []), ("p2p", 0, []), ("nccl", 1, []), ("nccl", 0, []),
@@ -445,21 +445,27 @@ def test_measured_fp32_peak_is_plausible(pkg):
 # ------------------------------------------------------------------ pair-symmetric pass
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("n", [1, 300, 1024, 5000, 9473])
-@pytest.mark.parametrize("seg_tiles,sym_ti", [(0, 4), (1, 4), (5, 8), (0, 8)])
-def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, seg_tiles, sym_ti):
+@pytest.mark.parametrize("prec,seg_tiles,sym_ti", [(32, 0, 4), (32, 1, 4), (32, 5, 8), (32, 0, 8), (64, 0, 4), (64, 3, 4)])
+def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, prec, seg_tiles, sym_ti):
     """Each unordered pair evaluated once (both reactions) must reproduce the ordered-pair pass and
     the oracle: forces, and a few fused steps through the finish kernel; ragged sizes, duplicates."""
     b = pkg.generators.uniform_cube(n, dim, seed=31 + n)
     if n >= 300:
         b[17, :dim] = b[3, :dim]                       # exact duplicate
         b[101, :dim] = b[100, :dim] + 2e-6             # pair under the cut-off (r^2 = 1.2e-11 < 1e-10)
-    b = pkg.generators.round_to_float(b)
+    if prec == 32:
+        b = pkg.generators.round_to_float(b)
     opts = {"detect": 1, "seg_tiles": seg_tiles}
-    f_sym = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32, options=dict(opts, symmetric=1, sym_ti=sym_ti))
-    f_ord = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32, options=dict(opts, symmetric=0))
-    assert_fp32_parity(pkg, oracle, f_sym, b, f"symmetric n={n}")
-    assert_fp32_parity(pkg, oracle, f_ord, b, f"ordered n={n}")
-    with pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as ctx:
+    f_sym = pkg.brute_force_cuda_n_body(b, prec, options=dict(opts, symmetric=1, sym_ti=sym_ti))
+    f_ord = pkg.brute_force_cuda_n_body(b, prec, options=dict(opts, symmetric=0))
+    if prec == 32:
+        assert_fp32_parity(pkg, oracle, f_sym, b, f"symmetric n={n}")
+        assert_fp32_parity(pkg, oracle, f_ord, b, f"ordered n={n}")
+    else:
+        ref = oracle.forces(b)
+        assert rel(pkg, f_sym, ref).max() <= TOL64
+        assert rel(pkg, f_ord, ref).max() <= TOL64
+    with pkg.NBodyCuda(dim, n, prec) as ctx:
         ctx.set_option("detect", 1)
         ctx.set_option("symmetric", 1)
         ctx.set_option("sym_ti", sym_ti)
@@ -469,6 +475,6 @@ def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, seg_tiles
         ctx.step(1e-5, 3)
         got = b.copy()
         ctx.download(got)
-    want = pkg.brute_force_cuda_simulate(b, 1e-5, 3, pkg.NB200_FP32, options=dict(opts, symmetric=0))
+    want = pkg.brute_force_cuda_simulate(b, 1e-5, 3, prec, options=dict(opts, symmetric=0))
     scale = np.abs(want[:, :2 * dim]).max()
-    assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= 2e-6 * scale
+    assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= (2e-6 if prec == 32 else 1e-12) * scale
