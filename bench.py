@@ -4,7 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n N] [--precision 32|64]
 
 One "step" = one pass of the hot path over all N bodies: all N(N-1) ordered interactions plus
-the per-body update (v += F/m dt; x += v dt).  Workload at every GPU count = BASELINE.json
+the per-body update (v += F/m dt; x += v dt).  The metric counts ORDERED interactions delivered
+(SURVEY 8d): the pair-symmetric pass evaluates each unordered pair once and feeds both bodies,
+exactly like the reference's own j > i loop (methods.cpp:18-39), and is credited with both.  Workload at every GPU count = BASELINE.json
 configs[4]: 3D, N = 1,048,576 bodies in a uniform cube (strong scaling: N is fixed, targets are
 sharded over the GPUs).  For --gpus N > 1 launch under torchrun, one rank per GPU.
 
@@ -360,7 +362,8 @@ def run_product_arm(args) -> None:
         "peak_measured": round(measured_peak, 2) if measured_peak else None,
         "frac_of_measured": round(achieved_tflops / measured_peak, 4) if measured_peak else None,
         "peak_measured_source": "nb200_measure_fp32_peak: independent packed FFMA2 chains timed with CUDA events in this run",
-        "fma_pipe_lane_ops_per_interaction": 11,
+        # ordered pass: 11 FMA-pipe lane-ops per interaction; pair-symmetric pass: 15 per pair of interactions
+        "fma_pipe_lane_ops_per_interaction": 7.5 if "pair-symmetric" in plan else 11,
         "traffic": traffic, "traffic_source": traffic_src,
         "hbm_algorithmic_bytes_per_step": n * (16 if prec == 32 else 32) + n * (2 * DIM * 8 * 2 + 8 + 3 * 8 * 2),
     }
@@ -371,7 +374,9 @@ def run_product_arm(args) -> None:
         "vs_baseline": None, "dtype": "f32" if prec == 32 else "f64", "data": "synthetic",
         "config": {"workload": f"c5: brute-force 3D uniform cube, N={n}, fused force+integrate step, dt={DT}",
                    "n": n, "dim": DIM, "precision": prec,
-                   "parallelism": f"targets sharded over {world} GPU(s); new positions stored into the peers' buffers over NVLink by the integrator epilogue" if world > 1 else "1 GPU",
+                   "parallelism": (f"targets sharded over {world} GPU(s); each block of pairs evaluated by one of its two "
+                                   "ranks, reaction sums and new positions stored into the peers' buffers over NVLink"
+                                   if world > 1 else "1 GPU"),
                    "l2": "flushed between timed steps (256 MiB write)", "plan": plan},
         "pipelined": {"value": round(pipelined, 2), "ms_per_step": round(pipe_ms / args.steps, 3),
                       "note": "same K steps in one nb200_step call, no L2 flush"},
