@@ -118,18 +118,23 @@ __device__ __forceinline__ void nb_tile_f32_sym(const float* __restrict__ stage,
     const bool writer = reducer && hh == 0;
     auto reduce_store = [&](int q_done, int buf) {
         const float* rb = rbase + buf * (32 * NB_SYM_ROW);
-        float v0 = 0.f, v1 = 0.f;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 16; k += 2) {
+        for (int k = 0; k < 16; k += 4) {
             v0 += rb[(2 * k) * NB_SYM_ROW];
             v1 += rb[(2 * k + 2) * NB_SYM_ROW];
+            v2 += rb[(2 * k + 4) * NB_SYM_ROW];
+            v3 += rb[(2 * k + 6) * NB_SYM_ROW];
         }
-        float v = v0 + v1;
+        float v = (v0 + v1) + (v2 + v3);
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         if (writer && q_done >= 0) wbase[q_done * 4] = v;
     };
 
-#pragma unroll 1
+#ifndef NB_SYM_UNROLL
+#define NB_SYM_UNROLL 1
+#endif
+    NB_UNROLL(NB_SYM_UNROLL)
     for (int q = 0; q < NB_TILE / 4; ++q) {
         const float4 X = sx[q], Y = sy[q], M = sm[q];
         float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
