@@ -115,6 +115,13 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
  * pairs under the cut-off excluded).  Rank contexts return their shard's partial sums. */
 int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, double* potential);
 
+/* Test aid (pure host logic, no device needed): the work list of the pair-symmetric pass for
+ * `rank` of `world` over n bodies, 4 ints per row: {i-tile, first source tile, end source tile,
+ * flags (bit 0: pair-symmetric row; clear: ordered pairs)}.  i-tiles are 1024 targets = 4 source
+ * tiles of 256, counted from the rank's first tile.  Writes at most `cap` rows, returns the row
+ * count (or a negative NB200_E* code). */
+int nb200_debug_sym_rows(size_t n, int world, int rank, int* rows_out, int cap);
+
 /* Measurement aid: the FP32 FMA-pipe throughput this device sustains on independent packed
  * FFMA2 chains (TFLOP/s, 2 flops per lane-op), timed with CUDA events.  It is the denominator of
  * the FP32 roofline fraction bench.py reports next to the nominal SMs x 128 x 2 x clock figure. */

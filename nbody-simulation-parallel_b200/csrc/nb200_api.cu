@@ -595,14 +595,12 @@ int peer_index(const Shard& s, int rank) {
     return -1;
 }
 
-int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg, bool cross) {
-    const int G = cross ? ctx->world : 1;
-    if (!s.sym_rows_host.empty() && s.sym_key_seg == seg && s.sym_key_world == G) return NB200_OK;
+// The work list of rank g of G (pure host logic, also exported for the CPU tests as
+// nb200_debug_sym_rows): shard g owns source tiles [g*T, (g+1)*T).
+void sym_rows_for(int g, int G, int T, std::vector<NbSymRow>& rows) {
     const int tpi = NB_SYM_ITILE / NB_TILE;                      // source tiles per i-tile
-    const int lo = (int)s.tile_lo, hi = (int)s.tile_hi;
-    const int T = (int)ctx->tiles_per_shard;
-    const int n_it = (hi - lo + tpi - 1) / tpi;
-    std::vector<NbSymRow>& rows = s.sym_rows_host;
+    const int lo = g * T, hi = (g + 1) * T;
+    const int n_it = (T + tpi - 1) / tpi;
     rows.clear();
     for (int it = 0; it < n_it; ++it) {
         const int d0 = lo + it * tpi, d1 = std::min(d0 + tpi, hi);
@@ -610,7 +608,6 @@ int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg, bool cross) {
         if (d1 < hi) rows.push_back(NbSymRow{it, d1, hi, NB_ROW_SYM});
     }
     if (G > 1) {
-        const int g = s.rank;
         for (int off = 1; off <= (G - 1) / 2; ++off) {
             const int h = (g + off) % G;
             for (int it = 0; it < n_it; ++it) rows.push_back(NbSymRow{it, h * T, (h + 1) * T, NB_ROW_SYM});
@@ -629,6 +626,13 @@ int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg, bool cross) {
             }
         }
     }
+}
+
+int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg, bool cross) {
+    const int G = cross ? ctx->world : 1;
+    if (!s.sym_rows_host.empty() && s.sym_key_seg == seg && s.sym_key_world == G) return NB200_OK;
+    std::vector<NbSymRow>& rows = s.sym_rows_host;
+    sym_rows_for(cross ? s.rank : 0, G, (int)ctx->tiles_per_shard, rows);
     if ((int)rows.size() > s.sym_rows_cap) return fail(ctx, NB200_ESTATE, "symmetric work list overflow");
     s.sym_prefix_host.assign(rows.size() + 1, 0);
     for (size_t r = 0; r < rows.size(); ++r)
@@ -1421,6 +1425,21 @@ int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, do
     *kinetic = ke;
     *potential = pe;
     return NB200_OK;
+}
+
+int nb200_debug_sym_rows(size_t n, int world, int rank, int* rows_out, int cap) {
+    if (world < 1 || rank < 0 || rank >= world || (cap > 0 && !rows_out)) return NB200_EINVAL;
+    const long long tiles = std::max<long long>(1, ((long long)n + NB_TILE - 1) / NB_TILE);
+    const int T = (int)((tiles + world - 1) / world);
+    std::vector<NbSymRow> rows;
+    sym_rows_for(rank, world, T, rows);
+    for (int r = 0; r < (int)rows.size() && r < cap; ++r) {
+        rows_out[4 * r + 0] = rows[r].it;
+        rows_out[4 * r + 1] = rows[r].t_begin;
+        rows_out[4 * r + 2] = rows[r].t_end;
+        rows_out[4 * r + 3] = rows[r].flags;
+    }
+    return (int)rows.size();
 }
 
 int nb200_measure_fp32_peak(int device, double* tflops) {

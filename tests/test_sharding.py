@@ -79,3 +79,41 @@ def test_stratified_generator_keeps_bodies_apart(pkg):
         r = np.sqrt((d * d).sum(-1))
         r[r == 0] = np.inf
         assert r.min() >= 0.5 / k - 1e-12
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("n", [1, 1000, 16384, 29000, 262144, 1 << 20])
+def test_pair_symmetric_work_lists_cover_every_pair_once(pkg, lib, n, world):
+    """Host logic of the cross-rank pair-symmetric pass (nb_force_sym.cuh / build_sym_rows): over all
+    ranks, every ordered (target tile, source tile) pair must be delivered exactly once -- by an
+    ordered row, or by a symmetric row that serves both directions -- and every rank must get the
+    same share of the work."""
+    import ctypes
+    tile, tpi = 256, 4
+    tiles = max(1, -(-n // tile))
+    T = -(-tiles // world)
+    NT = T * world
+    cover = np.zeros((NT, NT), dtype=np.int32)         # [target tile, source tile] deliveries
+    work = []
+    for rank in range(world):
+        cap = 8 * (T // tpi + 2)
+        buf = (ctypes.c_int * (4 * cap))()
+        nrows = lib.nb200_debug_sym_rows(n, world, rank, buf, cap)
+        assert 0 < nrows <= cap
+        rows = np.frombuffer(buf, dtype=np.int32)[:4 * nrows].reshape(nrows, 4)
+        w = 0
+        for it, t0, t1, flags in rows:
+            i0 = rank * T + it * tpi
+            i1 = min(i0 + tpi, (rank + 1) * T)         # lanes past the shard are inert
+            assert 0 <= t0 < t1 <= NT and i0 < i1
+            cover[i0:i1, t0:t1] += 1
+            if flags & 1:
+                cover[t0:t1, i0:i1] += 1               # the reaction: sources become targets
+                assert t0 >= i1 or t1 <= i0            # a symmetric row never holds its own i-tile
+            w += (i1 - i0) * (t1 - t0)
+        work.append(w)
+    assert cover.min() == 1 and cover.max() == 1
+    if T % (2 * tpi) == 0:                             # whole i-tiles and an even split of the opposite block
+        assert max(work) == min(work)
+    else:
+        assert max(work) - min(work) <= 2 * tpi * T
