@@ -127,9 +127,18 @@ int nb200_debug_sym_rows(size_t n, int world, int rank, int* rows_out, int cap);
  * the FP32 roofline fraction bench.py reports next to the nominal SMs x 128 x 2 x clock figure. */
 int nb200_measure_fp32_peak(int device, double* tflops);
 
-/* utils.h:170-219 on the host-resident arrays (n*D doubles each): percentage of bodies whose
- * every component is within 1 % of the reference (absolute 1e-9 test when |ref| < 1e-20). */
+/* compute_accuracy_omp<D> (utils.h:170-219), evaluated on the device: percentage of bodies whose
+ * every force component is within 1 % of the reference component (|reference| < 1e-20: |force|
+ * <= 1e-9 instead).  `reference` = n*D doubles on the host.  `forces` = n*D doubles on the host, or
+ * NULL to compare the forces of the last nb200_forces call that are still on the device (no
+ * download).  Rank contexts count their own rows only: the per-rank values add up to the total. */
 int nb200_accuracy_pct(nb200_ctx* ctx, const double* forces, const double* reference, double* pct);
+
+/* print_validation_forces<D> (utils.h:138-151) without downloading all forces: the forces of the
+ * bodies the reference prints (0-based i with (i+1) % (n/3) == 0) from the last nb200_forces
+ * call.  forces_out = cap*D doubles, index_out = cap body indices; returns the number of bodies
+ * written (rank contexts: the ones they own), 0 when n < 3, or a negative NB200_E* code. */
+int nb200_validation_forces(nb200_ctx* ctx, double* forces_out, long long* index_out, int cap);
 
 /* ---- introspection / measurement --------------------------------------------------------- */
 

@@ -133,13 +133,28 @@ class NBodyCuda:
         self._check(self._lib.nb200_energy(self._h, G, cutoff, ctypes.byref(ke), ctypes.byref(pe)), "energy")
         return ke.value, pe.value
 
-    def accuracy_pct(self, forces: np.ndarray, reference: np.ndarray) -> float:
-        f = np.ascontiguousarray(forces, dtype=np.float64)
+    def accuracy_pct(self, forces: np.ndarray | None, reference: np.ndarray) -> float:
+        """compute_accuracy_omp (utils.h:170-219) on the device; ``forces=None`` compares the forces of
+        the last ``forces()`` call that are still on the device."""
         r = np.ascontiguousarray(reference, dtype=np.float64)
+        fp = None
+        if forces is not None:
+            f = np.ascontiguousarray(forces, dtype=np.float64)
+            fp = f.ctypes.data_as(_lib._dp)
         pct = ctypes.c_double()
-        self._check(self._lib.nb200_accuracy_pct(self._h, f.ctypes.data_as(_lib._dp), r.ctypes.data_as(_lib._dp),
-                                                 ctypes.byref(pct)), "accuracy_pct")
+        self._check(self._lib.nb200_accuracy_pct(self._h, fp, r.ctypes.data_as(_lib._dp), ctypes.byref(pct)),
+                    "accuracy_pct")
         return pct.value
+
+    def validation_forces(self, cap: int = 8) -> tuple[np.ndarray, np.ndarray]:
+        """The (index, force) rows print_validation_forces (utils.h:138-151) would print."""
+        out = np.zeros((cap, self.dim))
+        idx = np.zeros(cap, dtype=np.int64)
+        k = self._lib.nb200_validation_forces(self._h, out.ctypes.data_as(_lib._dp),
+                                              idx.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), cap)
+        if k < 0:
+            self._check(k, "validation_forces")
+        return idx[:k], out[:k]
 
     # -- measurement
     @property

@@ -148,6 +148,8 @@ struct Shard {
     size_t aos_bytes = 0;
     unsigned long long* bounds = nullptr; // [2] bit patterns of max |coordinate|, max |mass| of the image
     double* energy = nullptr;             // [2]
+    double* cmp = nullptr;                // [2][n_local*D] staging of host force arrays for nb200_accuracy_pct
+    bool forces_valid = false;            // s.forces holds the result of the last nb200_forces call
     unsigned *tile_done = nullptr, *sched = nullptr;
     ncclComm_t comm_nccl = nullptr;
     int sms = 0;
@@ -337,7 +339,7 @@ void free_shard(Shard& s) {
     cudaFree(s.grid_keys); cudaFree(s.grid_counts); cudaFree(s.suspect); cudaFree(s.sym_rows); cudaFree(s.sym_prefix); cudaFree(s.gacc); cudaFree(s.sym_done);
     for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
     cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
-    cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.bounds); cudaFree(s.tile_done); cudaFree(s.sched);
+    cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.bounds); cudaFree(s.cmp); cudaFree(s.tile_done); cudaFree(s.sched);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
     if (s.ev_pass_done) cudaEventDestroy(s.ev_pass_done);
@@ -1231,6 +1233,7 @@ int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out)
         }
         if (rc) return rc;
         CK(cudaEventRecord(s.ev_stop, s.compute));
+        s.forces_valid = true;
         if (s.n_local > 0)
             CK(cudaMemcpyAsync(forces_out + (size_t)s.tgt_base * D, s.forces, (size_t)s.n_local * D * sizeof(double),
                                cudaMemcpyDeviceToHost, s.compute));
@@ -1475,20 +1478,58 @@ int nb200_measure_fp32_peak(int device, double* tflops) {
 }
 
 int nb200_accuracy_pct(nb200_ctx* ctx, const double* forces, const double* reference, double* pct) {
-    if (!ctx || !pct || (ctx->n && (!forces || !reference))) return NB200_EINVAL;
+    if (!ctx || !pct || (ctx->n && !reference)) return NB200_EINVAL;
     const int D = ctx->dim;
-    size_t ok = 0;
-    for (size_t i = 0; i < ctx->n; ++i) {
-        bool good = true;
-        for (int d = 0; d < D && good; ++d) {
-            const double r = reference[i * D + d], f = forces[i * D + d];
-            if (fabs(r) < 1e-20) good = !(fabs(f) > 1e-9);
-            else good = !(fabs((f - r) / r) > 0.01);
+    unsigned long long ok = 0;
+    for (Shard& s : ctx->shards) {
+        if (s.n_local <= 0) continue;
+        if (!forces && !s.forces_valid)
+            return fail(ctx, NB200_ESTATE, "accuracy of the device-resident forces needs a preceding nb200_forces call");
+        CK(cudaSetDevice(s.device));
+        const size_t cnt = (size_t)s.n_local * D;
+        if (!s.cmp) CK(cudaMalloc(&s.cmp, 2 * cnt * sizeof(double)));
+        CK(cudaMemcpyAsync(s.cmp, reference + (size_t)s.tgt_base * D, cnt * sizeof(double), cudaMemcpyHostToDevice, s.compute));
+        const double* f = s.forces;
+        if (forces) {
+            CK(cudaMemcpyAsync(s.cmp + cnt, forces + (size_t)s.tgt_base * D, cnt * sizeof(double), cudaMemcpyHostToDevice, s.compute));
+            f = s.cmp + cnt;
         }
-        ok += good;
+        CK(cudaMemsetAsync(s.bounds, 0, sizeof(unsigned long long), s.compute));
+        const int blocks = (int)((s.n_local + 255) / 256);
+        if (D == 3) nb_accuracy_kernel<3><<<blocks, 256, 0, s.compute>>>(f, s.cmp, s.n_local, s.bounds);
+        else nb_accuracy_kernel<2><<<blocks, 256, 0, s.compute>>>(f, s.cmp, s.n_local, s.bounds);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        unsigned long long h = 0;
+        CK(cudaMemcpyAsync(&h, s.bounds, sizeof h, cudaMemcpyDeviceToHost, s.compute));
+        CK(cudaStreamSynchronize(s.compute));
+        ok += h;
     }
     *pct = ctx->n ? 100.0 * (double)ok / (double)ctx->n : 0.0;
     return NB200_OK;
+}
+
+int nb200_validation_forces(nb200_ctx* ctx, double* forces_out, long long* index_out, int cap) {
+    if (!ctx || cap < 0 || (cap > 0 && (!forces_out || !index_out))) return NB200_EINVAL;
+    const int D = ctx->dim;
+    const long long n = (long long)ctx->n;
+    if (n < 3) return 0;                           // the reference divides by n / 3 (utils.h:142)
+    const long long stride = n / 3;
+    int count = 0;
+    for (long long i = stride - 1; i < n && count < cap; i += stride) {   // (i + 1) % (n / 3) == 0
+        for (Shard& s : ctx->shards) {
+            if (i < s.tgt_base || i >= s.tgt_base + s.n_local) continue;
+            if (!s.forces_valid)
+                return fail(ctx, NB200_ESTATE, "validation forces need a preceding nb200_forces call");
+            CK(cudaSetDevice(s.device));
+            CK(cudaMemcpyAsync(forces_out + (size_t)count * D, s.forces + (size_t)(i - s.tgt_base) * D,
+                               D * sizeof(double), cudaMemcpyDeviceToHost, s.compute));
+            CK(cudaStreamSynchronize(s.compute));
+            index_out[count] = i;
+            ++count;
+        }
+    }
+    return count;
 }
 
 }  // extern "C"

@@ -234,6 +234,29 @@ __global__ void nb_grid_query_kernel(const real* __restrict__ src, long long tgt
 }
 
 // ---------------------------------------------------------------------------------------------
+// compute_accuracy_omp<D> (utils.h:170-219) on the device: a body counts as accurate when EVERY
+// component is within 1 % of the reference component; reference components under 1e-20 in
+// magnitude are held to |force| <= 1e-9 instead (utils.h:25-26, :191-197).
+template <int D>
+__global__ void __launch_bounds__(256) nb_accuracy_kernel(const double* __restrict__ forces,
+                                                           const double* __restrict__ reference,
+                                                           long long n, unsigned long long* __restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool good = false;
+    if (i < n) {
+        good = true;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const double r = reference[i * D + d], f = forces[i * D + d];
+            if (fabs(r) < 1e-20) good = good && !(fabs(f) > 1e-9);
+            else good = good && !(fabs((f - r) / r) > 0.01);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, good);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Measured FP32 FMA-pipe peak of the device the roofline is quoted against (MEASURED_PEAKS.json
 // holds only HBM and bf16-tensor peaks): independent packed FFMA2 chains acc = x*x + acc, eight per
 // thread, two operands each so the register file is not the limit (tools/ubench.cu: 97 % of

@@ -478,3 +478,29 @@ def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, prec, seg
     want = pkg.brute_force_cuda_simulate(b, 1e-5, 3, prec, options=dict(opts, symmetric=0))
     scale = np.abs(want[:, :2 * dim]).max()
     assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= (2e-6 if prec == 32 else 1e-12) * scale
+
+
+# ------------------------------------------------------------------ -a 1 column and validation print on the device
+@pytest.mark.parametrize("dim,n", [(3, 3001), (2, 1000), (3, 5)])
+def test_device_side_accuracy_and_validation_forces(pkg, oracle, dim, n):
+    """compute_accuracy_omp / print_validation_forces (utils.h:138-219) evaluated against the forces
+    still resident on the device: same percentage as the reference's metric on the host arrays, and
+    exactly the bodies the reference would print ((i+1) % (n/3) == 0)."""
+    b = pkg.generators.uniform_cube(n, dim, seed=9)
+    ref = oracle.forces(b)
+    bad = ref.copy()
+    bad[::10] *= 1.05                                   # every 10th body off by 5 %: fails the 1 % test
+    with pkg.NBodyCuda(dim, n) as ctx:
+        ctx.upload(b)
+        with pytest.raises(pkg.NB200Error):
+            ctx.accuracy_pct(None, ref)                 # nothing resident yet
+        f = ctx.forces()
+        assert ctx.accuracy_pct(None, ref) == 100.0
+        assert ctx.accuracy_pct(f, ref) == 100.0
+        want = oracle.accuracy_pct(f, bad)
+        assert ctx.accuracy_pct(None, bad) == pytest.approx(want, abs=1e-9)
+        assert ctx.accuracy_pct(bad, ref) == pytest.approx(oracle.accuracy_pct(bad, ref), abs=1e-9)
+        idx, vf = ctx.validation_forces(cap=8)
+        expect = [i for i in range(n) if (i + 1) % (n // 3) == 0][:8]
+        assert list(idx) == expect
+        assert np.array_equal(vf, f[expect])
