@@ -87,6 +87,18 @@ void nb200_destroy(nb200_ctx* ctx);
  * stride in bytes (40 for D=2, 56 for D=3, or larger).  Every rank passes ALL n bodies. */
 int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride);
 
+/* Seeded synthetic bodies generated ON the device instead of uploaded (same state afterwards as
+ * nb200_upload_aos of the same bodies with the packed 40/56-byte stride; read them back with
+ * nb200_download_aos).  The reference's generate_random_bodies<D> (utils.h:107-135) is unseeded;
+ * kind 0 reproduces its ranges (pos U[1,1e7], vel U[-10,10], mass U[1,1e8], utils.h:113-115), kind 1
+ * is the uniform unit cube/square (vel U[-0.1,0.1], mass U[0.5,1.5]/(G n)), kind 2 the 3D Plummer
+ * sphere (equal masses 1/(G n)).  Bodies depend only on (kind, seed, n, G, body index) --
+ * Philox-4x32-10 -- so every rank of a sharded run generates the same set. */
+#define NB200_GEN_REFERENCE_RANGE 0
+#define NB200_GEN_UNIFORM 1
+#define NB200_GEN_PLUMMER 2
+int nb200_generate(nb200_ctx* ctx, int kind, unsigned long long seed, double G);
+
 /* Writes position and velocity of the bodies this context owns back into an AoS array of ALL n
  * bodies: every body for nb200_create contexts, rows [lo,hi) of nb200_shard_range for
  * nb200_create_rank contexts.  Same stride as the upload.  With packed records (stride 40 / 56)

@@ -106,6 +106,12 @@ class NBodyCuda:
                     "upload")
         self._stride = b.strides[0] if self.n else 8 * (2 * self.dim + 1)
 
+    def generate(self, kind: int, seed: int, G: float = G_REF):
+        """Seeded bodies generated on the device (nb200_generate): 0 reference range, 1 uniform, 2 Plummer.
+        ``generators.device_bodies`` is the numpy mirror of the same generator."""
+        self._check(self._lib.nb200_generate(self._h, int(kind), int(seed), float(G)), "generate")
+        self._stride = 8 * (2 * self.dim + 1)
+
     def download(self, into: np.ndarray) -> np.ndarray:
         """Overwrite the owned rows of ``into`` with the advanced bodies (mass = the uploaded mass)."""
         if into.dtype != np.float64 or not into.flags.c_contiguous or into.shape != (self.n, 2 * self.dim + 1):

@@ -34,6 +34,7 @@ SIGNATURES = {
     "nb200_destroy": (None, [_ctx_p]),
     "nb200_upload_aos": (_c.c_int, [_ctx_p, _c.c_void_p, _c.c_size_t]),
     "nb200_download_aos": (_c.c_int, [_ctx_p, _c.c_void_p, _c.c_size_t]),
+    "nb200_generate": (_c.c_int, [_ctx_p, _c.c_int, _c.c_ulonglong, _c.c_double]),
     "nb200_shard_range": (_c.c_int, [_ctx_p, _c.POINTER(_c.c_size_t), _c.POINTER(_c.c_size_t)]),
     "nb200_forces": (_c.c_int, [_ctx_p, _c.c_double, _c.c_double, _dp]),
     "nb200_step": (_c.c_int, [_ctx_p, _c.c_double, _c.c_double, _c.c_double, _c.c_int]),

@@ -914,6 +914,40 @@ int publish_epoch(nb200_ctx* ctx) {
     return NB200_OK;
 }
 
+// common tail of nb200_upload_aos / nb200_generate: the AoS image is in aos_dev on every shard
+int finish_upload(nb200_ctx* ctx) {
+    const int D = ctx->dim;
+    const size_t sd = ctx->aos_stride / sizeof(double);
+    if (ctx->n) {
+        // bounds of the image, reduced on the device that already holds it (shard 0)
+        Shard& s = ctx->shards[0];
+        CK(cudaSetDevice(s.device));
+        CK(cudaMemsetAsync(s.bounds, 0, 2 * sizeof(unsigned long long), s.compute));
+        const int blocks = (int)std::min<long long>(4LL * s.sms, ((long long)ctx->n + 255) / 256);
+        if (D == 3) nb_bounds_kernel<3><<<blocks, 256, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, s.bounds);
+        else nb_bounds_kernel<2><<<blocks, 256, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, s.bounds);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        double hb[2] = {0.0, 0.0};
+        CK(cudaMemcpyAsync(hb, s.bounds, sizeof hb, cudaMemcpyDeviceToHost, s.compute));
+        CK(cudaStreamSynchronize(s.compute));
+        const double xmax = hb[0], mmax = hb[1];
+        int ex = 0;
+        if (xmax > 0 && isfinite(xmax)) ctx->xmax = xmax;
+        if (!ctx->f64) {
+            if (xmax > 0 && isfinite(xmax)) { frexp(xmax, &ex); ctx->pos_scale = ldexp(1.0, -ex); }
+            if (mmax > 0 && isfinite(mmax)) { frexp(mmax, &ex); ctx->mass_scale = ldexp(1.0, -ex); }
+        }
+    }
+    int rc = pack_sources(ctx);
+    if (rc) return rc;
+    for (Shard& s : ctx->shards) s.forces_valid = false;
+    ctx->pristine = true;
+    ctx->cur = 0;
+    ctx->uploaded = true;
+    return NB200_OK;
+}
+
 }  // namespace
 
 // =============================================================================== C ABI
@@ -1127,7 +1161,6 @@ int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
     if (stride < min_stride || stride % sizeof(double))
         return fail(ctx, NB200_EINVAL, "stride %zu: Body<%d> needs >= %zu bytes, multiple of 8", stride, D, min_stride);
     ctx->aos_stride = stride;
-    const size_t sd = stride / sizeof(double);
     // FP32 pair math runs on power-of-two-scaled sources (exact): |x'| <= 1, m' <= 1
     ctx->pos_scale = ctx->mass_scale = 1.0;
     ctx->xmax = 1.0;
@@ -1138,33 +1171,34 @@ int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
         if (!s.aos_dev) { CK(cudaMalloc(&s.aos_dev, bytes)); s.aos_bytes = bytes; }
         if (ctx->n) CK(cudaMemcpyAsync(s.aos_dev, bodies, ctx->n * stride, cudaMemcpyHostToDevice, s.compute));
     }
-    if (ctx->n) {
-        // bounds of the image, reduced on the device that already holds it (shard 0)
-        Shard& s = ctx->shards[0];
+    return finish_upload(ctx);
+}
+
+int nb200_generate(nb200_ctx* ctx, int kind, unsigned long long seed, double G) {
+    if (!ctx) return NB200_EINVAL;
+    const int D = ctx->dim;
+    if (kind < 0 || kind > 2) return fail(ctx, NB200_EINVAL, "generator kind %d: 0 reference range, 1 uniform cube, 2 Plummer", kind);
+    if (kind == 2 && D != 3) return fail(ctx, NB200_EINVAL, "the Plummer generator is 3D only");
+    if (!(G > 0.0)) return fail(ctx, NB200_EINVAL, "G must be positive");
+    const size_t stride = (size_t)(2 * D + 1) * sizeof(double);
+    ctx->aos_stride = stride;
+    const size_t sd = stride / sizeof(double);
+    ctx->pos_scale = ctx->mass_scale = 1.0;
+    ctx->xmax = 1.0;
+    for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
-        CK(cudaMemsetAsync(s.bounds, 0, 2 * sizeof(unsigned long long), s.compute));
-        const int blocks = (int)std::min<long long>(4LL * s.sms, ((long long)ctx->n + 255) / 256);
-        if (D == 3) nb_bounds_kernel<3><<<blocks, 256, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, s.bounds);
-        else nb_bounds_kernel<2><<<blocks, 256, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, s.bounds);
-        CK(cudaGetLastError());
-        ctx->launches++;
-        double hb[2] = {0.0, 0.0};
-        CK(cudaMemcpyAsync(hb, s.bounds, sizeof hb, cudaMemcpyDeviceToHost, s.compute));
-        CK(cudaStreamSynchronize(s.compute));
-        const double xmax = hb[0], mmax = hb[1];
-        int ex = 0;
-        if (xmax > 0 && isfinite(xmax)) ctx->xmax = xmax;
-        if (!ctx->f64) {
-            if (xmax > 0 && isfinite(xmax)) { frexp(xmax, &ex); ctx->pos_scale = ldexp(1.0, -ex); }
-            if (mmax > 0 && isfinite(mmax)) { frexp(mmax, &ex); ctx->mass_scale = ldexp(1.0, -ex); }
+        const size_t bytes = std::max<size_t>(1, ctx->n) * stride;
+        if (s.aos_dev && s.aos_bytes < bytes) { CK(cudaFree(s.aos_dev)); s.aos_dev = nullptr; }
+        if (!s.aos_dev) { CK(cudaMalloc(&s.aos_dev, bytes)); s.aos_bytes = bytes; }
+        if (ctx->n) {
+            const int blocks = (int)((ctx->n + 255) / 256);
+            if (D == 3) nb_generate_kernel<3><<<blocks, 256, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, kind, seed, G);
+            else nb_generate_kernel<2><<<blocks, 256, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, kind, seed, G);
+            CK(cudaGetLastError());
+            ctx->launches++;
         }
     }
-    int rc = pack_sources(ctx);
-    if (rc) return rc;
-    ctx->pristine = true;
-    ctx->cur = 0;
-    ctx->uploaded = true;
-    return NB200_OK;
+    return finish_upload(ctx);
 }
 
 int nb200_download_aos(nb200_ctx* ctx, void* bodies, size_t stride) {

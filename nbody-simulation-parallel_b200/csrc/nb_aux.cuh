@@ -234,6 +234,88 @@ __global__ void nb_grid_query_kernel(const real* __restrict__ src, long long tgt
 }
 
 // ---------------------------------------------------------------------------------------------
+// Seeded body generators on the device.  The reference's generator
+// (generate_random_bodies<D>, utils.h:107-135) is unseeded; these reproduce its RANGES
+// (kind 0: pos U[1,1e7], vel U[-10,10], mass U[1,1e8], utils.h:113-115) and add the two
+// distributions BASELINE.json names (kind 1: uniform cube/square, kind 2: Plummer sphere), keyed by
+// (seed, body index) through Philox-4x32-10, so every shard/rank generates identical bytes and the
+// host mirror in generators.py (numpy) reproduces them for the oracle.  Output: the AoS Body<D>
+// image (position[D], velocity[D], mass) that nb200_upload_aos would have copied in.
+struct NbPhilox {
+    unsigned k0, k1;
+    __host__ __device__ static void mulhilo(unsigned a, unsigned b, unsigned& hi, unsigned& lo) {
+        const unsigned long long p = (unsigned long long)a * b;
+        hi = (unsigned)(p >> 32);
+        lo = (unsigned)p;
+    }
+    // two 53-bit uniforms in [0,1) from counter (index, stream)
+    __host__ __device__ void draw(unsigned long long index, unsigned stream, double& u0, double& u1) const {
+        unsigned c0 = (unsigned)index, c1 = (unsigned)(index >> 32), c2 = stream, c3 = 0u;
+        unsigned a = k0, b = k1;
+        for (int r = 0; r < 10; ++r) {
+            unsigned h0, l0, h1, l1;
+            mulhilo(0xD2511F53u, c0, h0, l0);
+            mulhilo(0xCD9E8D57u, c2, h1, l1);
+            const unsigned n0 = h1 ^ c1 ^ a, n1 = l1, n2 = h0 ^ c3 ^ b, n3 = l0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+        u0 = (double)((((unsigned long long)c0 << 32) | c1) >> 11) * 0x1.0p-53;
+        u1 = (double)((((unsigned long long)c2 << 32) | c3) >> 11) * 0x1.0p-53;
+    }
+};
+
+__device__ __forceinline__ double nb_lerp(double lo, double hi, double u) {
+    return __dadd_rn(lo, __dmul_rn(hi - lo, u));          // no FMA contraction: bit-identical to the host mirror
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) nb_generate_kernel(double* __restrict__ aos, size_t stride_d, long long n,
+                                                           int kind, unsigned long long seed, double G) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    NbPhilox rng{(unsigned)seed, (unsigned)(seed >> 32)};
+    double u[8];
+    for (int k = 0; k < 4; ++k) rng.draw((unsigned long long)i, (unsigned)k, u[2 * k], u[2 * k + 1]);
+    double* rec = aos + (size_t)i * stride_d;
+    if (kind == 0) {
+        for (int d = 0; d < D; ++d) rec[d] = nb_lerp(1.0, 1.0e7, u[d]);
+        for (int d = 0; d < D; ++d) rec[D + d] = nb_lerp(-10.0, 10.0, u[3 + d]);
+        rec[2 * D] = nb_lerp(1.0, 1.0e8, u[6]);
+    } else if (kind == 1) {
+        for (int d = 0; d < D; ++d) rec[d] = u[d];
+        for (int d = 0; d < D; ++d) rec[D + d] = nb_lerp(-0.1, 0.1, u[3 + d]);
+        rec[2 * D] = __ddiv_rn(nb_lerp(0.5, 1.5, u[6]), __dmul_rn(G, (double)n));
+    } else {
+        // Plummer sphere, scale 1, truncated at 22.8: r = (u^(-2/3) - 1)^(-1/2); speeds by the standard
+        // q^2 (1 - q^2)^(7/2) rejection times the escape speed sqrt(2) (1 + r^2)^(-1/4); equal masses
+        double r = 0.0, q = 0.0, a0, a1;
+        for (unsigned att = 0;; ++att) {
+            rng.draw((unsigned long long)i, 16u + att, a0, a1);
+            if (a0 > 0.0) {
+                r = 1.0 / sqrt(pow(a0, -2.0 / 3.0) - 1.0);
+                if (r < 22.8) break;
+            }
+        }
+        for (unsigned att = 0;; ++att) {
+            rng.draw((unsigned long long)i, 1024u + att, a0, a1);
+            if (0.1 * a1 < a0 * a0 * pow(1.0 - a0 * a0, 3.5)) { q = a0; break; }
+        }
+        const double speed = q * sqrt(2.0) * pow(1.0 + r * r, -0.25);
+        const double two_pi = 6.283185307179586;
+        const double z0 = 2.0 * u[0] - 1.0, p0 = two_pi * u[1], s0 = sqrt(1.0 - z0 * z0);
+        const double z1 = 2.0 * u[2] - 1.0, p1 = two_pi * u[3], s1 = sqrt(1.0 - z1 * z1);
+        const double dir0[3] = {s0 * cos(p0), s0 * sin(p0), z0}, dir1[3] = {s1 * cos(p1), s1 * sin(p1), z1};
+        for (int d = 0; d < D; ++d) {
+            rec[d] = dir0[d] * r;
+            rec[D + d] = dir1[d] * speed;
+        }
+        rec[2 * D] = __ddiv_rn(1.0, __dmul_rn(G, (double)n));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // compute_accuracy_omp<D> (utils.h:170-219) on the device: a body counts as accurate when EVERY
 // component is within 1 % of the reference component; reference components under 1e-20 in
 // magnitude are held to |force| <= 1e-9 instead (utils.h:25-26, :191-197).

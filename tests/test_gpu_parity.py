@@ -504,3 +504,29 @@ def test_device_side_accuracy_and_validation_forces(pkg, oracle, dim, n):
         expect = [i for i in range(n) if (i + 1) % (n // 3) == 0][:8]
         assert list(idx) == expect
         assert np.array_equal(vf, f[expect])
+
+
+# ------------------------------------------------------------------ seeded generators on the device
+@pytest.mark.parametrize("dim,kind", [(3, 0), (2, 0), (3, 1), (2, 1), (3, 2)])
+@pytest.mark.parametrize("prec", [64, 32])
+def test_device_generated_bodies_match_the_host_mirror(pkg, oracle, dim, kind, prec):
+    """nb200_generate: the bodies never cross PCIe; the numpy mirror reproduces them (bit for bit for
+    the arithmetic-only kinds), so the oracle sees the same input and the forces must agree."""
+    n = 6000
+    want = pkg.generators.device_bodies(n, dim, kind, seed=1234)
+    with pkg.NBodyCuda(dim, n, prec) as ctx:
+        ctx.generate(kind, 1234)
+        got = np.zeros((n, 2 * dim + 1))
+        ctx.download(got)
+        if kind < 2:
+            assert np.array_equal(got, want)
+        else:
+            assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+        f = ctx.forces()
+    if prec == 64:
+        assert rel(pkg, f, oracle.forces(got)).max() <= TOL64
+    else:
+        assert_fp32_parity(pkg, oracle, f, pkg.generators.round_to_float(got), f"generated kind {kind}")
+    with pkg.NBodyCuda(2, 10) as ctx:
+        with pytest.raises(pkg.NB200Error):
+            ctx.generate(2, 1)                          # Plummer is 3D only

@@ -117,3 +117,20 @@ def test_pair_symmetric_work_lists_cover_every_pair_once(pkg, lib, n, world):
         assert max(work) == min(work)
     else:
         assert max(work) - min(work) <= 2 * tpi * T
+
+
+def test_device_generator_mirror_known_answers(pkg):
+    """The numpy mirror of the device generator: Philox-4x32-10 known-answer vector (Random123:
+    counter 0, key 0 -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8) and the ranges of utils.h:113-115."""
+    g = pkg.generators
+    a, b = g._philox_uniforms(0, np.array([0], dtype=np.uint64), 0)
+    assert a[0] == (0x6627E8D5E169C58D >> 11) * 2.0 ** -53 and b[0] == (0xBC57AC4C9B00DBD8 >> 11) * 2.0 ** -53
+    r = g.device_bodies(20000, 3, 0, seed=3)
+    assert 1.0 <= r[:, :3].min() and r[:, :3].max() <= 1.0e7 and np.abs(r[:, 3:6]).max() <= 10.0
+    assert 1.0 <= r[:, 6].min() and r[:, 6].max() <= 1.0e8
+    u = g.device_bodies(20000, 2, 1, seed=3)
+    assert 0.0 <= u[:, :2].min() and u[:, :2].max() < 1.0 and abs(u[:, :2].mean() - 0.5) < 0.01
+    p = g.device_bodies(50000, 3, 2, seed=3)
+    rad = np.linalg.norm(p[:, :3], axis=1)
+    assert abs(np.median(rad) - 1.3048) < 0.02 and rad.max() < 22.8     # Plummer half-mass radius
+    assert not np.array_equal(g.device_bodies(100, 3, 1, seed=1), g.device_bodies(100, 3, 1, seed=2))
