@@ -8,6 +8,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "nb200.h"
 
@@ -103,10 +104,37 @@ void brute_force_cuda_simulate(std::vector<Body<D>>& bodies, double dt, int step
     nb200_last_elapsed_ms(ctx, &session().last_ms);
 }
 
+// One throw-away evaluation on a tiny body set per (dimension, precision): CUDA loads kernels lazily
+// on their first launch, which would otherwise land inside the first timed call of a process.
+void touch_kernels(int dim, int precision) {
+    static bool done[4][2] = {{false}};
+    bool& flag = done[dim][precision == NB200_FP32 ? 1 : 0];
+    if (flag) return;
+    flag = true;
+    const std::size_t n = 2048;
+    const int w = 2 * dim + 1;
+    std::vector<double> aos(n * w, 0.0);
+    for (std::size_t i = 0; i < n; ++i) {
+        for (int d = 0; d < dim; ++d) aos[i * w + d] = 1.0 + (double)((i * 2654435761u + d * 40503u) % 9973) / 9973.0;
+        aos[i * w + 2 * dim] = 1.0;
+    }
+    std::vector<double> f(n * dim);
+    nb200_ctx* t = nullptr;
+    if (nb200_create(&t, dim, n, precision, 1) != NB200_OK) return;
+    for (int pass = 0; pass < 2; ++pass) {          // the small-N kernels, then the pre-pass + pair-symmetric ones
+        nb200_set_option(t, "detect", pass);
+        if (nb200_upload_aos(t, aos.data(), w * sizeof(double)) != NB200_OK) break;
+        if (nb200_forces(t, kG, kCutoffR2, f.data()) != NB200_OK) break;
+    }
+    nb200_destroy(t);
+}
+
 template <int D>
 void brute_force_cuda_warmup(std::size_t n) {
     std::lock_guard<std::mutex> lock(session_mutex());
-    if (n) acquire(D, n);
+    if (!n) return;
+    acquire(D, n);
+    touch_kernels(D, env_int("NB200_PRECISION", NB200_FP64));
 }
 
 double brute_force_cuda_last_kernel_ms() { return session().last_ms; }
