@@ -138,6 +138,11 @@ def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the reference arm is the CPU implementation "with
+    # all the host threads it can use", and only rank 0 runs: give it the whole box back (libgomp reads
+    # the variable when the checker library is first loaded, below)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     oracle = entry.load_oracle()
     pkg = entry.load_package()
     n_s = min(args.n, CPU_SAMPLE_N)
