@@ -169,13 +169,13 @@ __device__ __forceinline__ void nb_tile_f32_sym(const float* __restrict__ stage,
                 const float2 w = __fmul2_rn(inv, inv);
                 const float2 s = __fmul2_rn(w, ms);
                 const float2 u = __fmul2_rn(w, make_float2(mi[t], mi[t]));
-                a[t][0] = __ffma2_rn(s, dx, a[t][0]);
-                b[h][0] = __ffma2_rn(u, dx, b[h][0]);
-                a[t][1] = __ffma2_rn(s, dy, a[t][1]);
-                b[h][1] = __ffma2_rn(u, dy, b[h][1]);
+                a[t][0] = __ffma2_rn(dx, s, a[t][0]);
+                b[h][0] = __ffma2_rn(dx, u, b[h][0]);
+                a[t][1] = __ffma2_rn(dy, s, a[t][1]);
+                b[h][1] = __ffma2_rn(dy, u, b[h][1]);
                 if (D == 3) {
-                    a[t][2] = __ffma2_rn(s, dz, a[t][2]);
-                    b[h][2] = __ffma2_rn(u, dz, b[h][2]);
+                    a[t][2] = __ffma2_rn(dz, s, a[t][2]);
+                    b[h][2] = __ffma2_rn(dz, u, b[h][2]);
                 }
             }
         }
