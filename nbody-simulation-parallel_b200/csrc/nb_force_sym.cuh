@@ -1,23 +1,28 @@
-// nb_force_sym.cuh -- the pair-symmetric flavour of the force pass (FP32).
+// nb_force_sym.cuh -- the pair-symmetric flavour of the force pass (FP32 and FP64).
 //
 // The reference's sequential variant walks only j > i and scatters +-force to both bodies
 // (brute_force_seq_n_body, methods.cpp:18-39: forces[j] += f; forces[i] -= f).  This kernel does
-// the same on the GPU for the block of pairs whose two bodies BOTH belong to this shard: every
-// unordered pair is evaluated once and feeds two accumulators, so the shared part of the chain
-// (3 FADD2 + FMUL2 + 2 FFMA2 for d and r^2, MUFU.RCP, FMUL2 for 1/r^4) is paid once per two
-// interactions: 15 packed FMA-pipe instructions per two pairs of bodies = 7.5 lane-ops per
-// ordered interaction instead of 11.
+// the same on the GPU: every unordered pair is evaluated once and feeds two accumulators, so the
+// shared part of the chain (3 FADD2 + FMUL2 + 2 FFMA2 for d and r^2, MUFU.RCP, FMUL2 for 1/r^4) is
+// paid once per two interactions: 15 packed FMA-pipe instructions per two pairs of bodies = 7.5
+// lane-ops per ordered interaction instead of 11 (FP64: 18 DP operations per pair instead of 28).
 //
-// Work units: (i-tile of 1024 own targets) x (segment of source tiles strictly ABOVE the
-// i-tile), plus one diagonal unit per i-tile (its own four source tiles, evaluated as ordered
-// pairs by the ordinary tile functions).  A thread keeps four targets in registers ("a" side,
-// summed per tile into FP64 exactly like nb_force_kernel); the reaction on the streamed sources
-// ("b" side) is produced per lane for four sources at a time and reduced
-//   lane partials -> warp  : through a 32x12 shared-memory transpose (3 STS.128, 16 LDS, 16 FADD)
+// Work list (built on the host, nb200_api.cu build_sym_rows): rows = (i-tile of 1024 own
+// targets) x (run of source tiles), cut into units of seg_tiles tiles.  Per i-tile one ORDERED row
+// (its own four source tiles, evaluated as ordered pairs by the tile functions of nb_force.cuh:
+// self pairs, exact cut-off) and one SYMMETRIC row (the own tiles above it); with several ranks
+// also the cross-shard blocks this rank is responsible for (its targets x another shard's sources).
+//
+// A thread keeps TI targets in registers ("a" side, summed per tile into FP64 exactly like
+// nb_force_kernel); the reaction on the streamed sources ("b" side) is produced per lane for four
+// sources (FP64: two) per iteration and reduced
+//   lane partials -> warp  : a 32 x 12-word shared-memory transpose (6 STS.64, 16 LDS, 16 FADD)
 //   warp sums     -> CTA   : per-warp [D][256] tile buffers, summed by the CTA after the tile
-//   CTA tile sums -> global: one FP64 atomicAdd per (source, component) per tile
+//   CTA tile sums -> global: one FP64 atomicAdd per (source, component) per tile, into an
+//                            accumulator array indexed by GLOBAL body (any body can receive)
 // The integrator/forces epilogue cannot be fused here (an i-tile also receives "b" sums from the
-// units of every lower i-tile), so nb_finish_kernel runs after the pass.
+// units of other i-tiles and, across ranks, from other GPUs: nb_sym_push_kernel), so
+// nb_finish_kernel runs after the pass.
 #pragma once
 #include "nb_force.cuh"
 
@@ -256,13 +261,13 @@ __device__ __forceinline__ void nb_tile_f64_sym(const double* __restrict__ stage
                 const double w = inv * inv;
                 const double s = w * ms;
                 const double u = w * mi[t];
-                accd[t][0] = fma(s, dx, accd[t][0]);
-                b[h][0] = fma(u, dx, b[h][0]);
-                accd[t][1] = fma(s, dy, accd[t][1]);
-                b[h][1] = fma(u, dy, b[h][1]);
+                accd[t][0] = fma(dx, s, accd[t][0]);
+                b[h][0] = fma(dx, u, b[h][0]);
+                accd[t][1] = fma(dy, s, accd[t][1]);
+                b[h][1] = fma(dy, u, b[h][1]);
                 if (D == 3) {
-                    accd[t][2] = fma(s, dz, accd[t][2]);
-                    b[h][2] = fma(u, dz, b[h][2]);
+                    accd[t][2] = fma(dz, s, accd[t][2]);
+                    b[h][2] = fma(dz, u, b[h][2]);
                 }
             }
         }
