@@ -654,8 +654,24 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     const bool cross = ctx->world > 1;
     const int W = ctx->world;
     const int tiles = (int)ctx->tiles_per_shard;
+    // two register-block shapes of the same 1024-target i-tile: 4 targets x 256 threads, 8 x 128
+    // (auto: the 2D chain is shorter, so the per-iteration reduction weighs more: 8 targets per thread there)
+    const int want_ti = ctx->opt_sym_ti ? ctx->opt_sym_ti : (D == 2 ? 8 : 4);
+    const int ti = (!ctx->f64 && want_ti == 8) ? 8 : 4;
+    const int block = NB_SYM_ITILE / ti;
+    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, ti);
+    const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64);
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kfn, block, smem));
+    const int resident = std::max(1, nb) * s.sms;
     int seg = ctx->opt_seg_tiles;
-    if (seg <= 0) seg = tiles * (cross ? W : 1) <= 1024 ? 8 : tiles * (cross ? W : 1) <= 2048 ? 16 : 32;
+    if (seg <= 0) {
+        // this rank evaluates ~ n_it * NT/2 (i-tile, source tile) cells: aim for ~32 units per resident CTA
+        // (tail balance) without going under 2 tiles per unit (per-unit start-up) or over 32
+        const long long n_it = (tiles + NB_SYM_ITILE / NB_TILE - 1) / (NB_SYM_ITILE / NB_TILE);
+        const long long cells = n_it * (long long)ctx->ntiles / 2;
+        seg = (int)std::max<long long>(2, std::min<long long>(32, cells / (32LL * resident)));
+    }
     if (int rc = build_sym_rows(ctx, s, seg, cross)) return rc;
     NbSymParams Q;
     memset(&Q, 0, sizeof Q);
@@ -672,16 +688,7 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     Q.seg_tiles = seg;
     Q.total_units = s.sym_prefix_host.back();
     Q.cutoff = cutoff * ctx->pos_scale * ctx->pos_scale;
-    // two register-block shapes of the same 1024-target i-tile: 4 targets x 256 threads, 8 x 128
-    // auto: the 2D chain is shorter, so the per-iteration reduction weighs more: 8 targets per thread there
-    const int want_ti = ctx->opt_sym_ti ? ctx->opt_sym_ti : (D == 2 ? 8 : 4);
-    const int ti = (!ctx->f64 && want_ti == 8) ? 8 : 4;
-    const int block = NB_SYM_ITILE / ti;
-    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, ti);
-    const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64);
-    int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kfn, block, smem));
-    const int grid = std::min(std::max(1, nb) * s.sms, Q.total_units);
+    const int grid = std::min(resident, Q.total_units);
     kfn<<<grid, block, smem, s.compute>>>(Q);
     CK(cudaGetLastError());
     ctx->launches++;
