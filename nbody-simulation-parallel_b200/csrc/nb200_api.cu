@@ -392,7 +392,7 @@ struct Plan {
 // from N ~ 32768 up (3D FP32: 2323 vs 2245 G inter/s there, 2887 vs 2394 at 49152)
 bool use_detect(const nb200_ctx* ctx) {
     if (ctx->opt_detect >= 0) return ctx->opt_detect != 0;
-    return ctx->n >= 32768;
+    return ctx->n >= ((ctx->f64 || ctx->dim == 2) ? 24576u : 32768u);   // FP64 / 2D: 1077 vs 974, 2953 vs 2762 at 24576
 }
 
 int make_plan(nb200_ctx* ctx, const Shard& s, Plan* out) {
