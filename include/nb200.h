@@ -176,6 +176,8 @@ long long nb200_launch_count(const nb200_ctx* ctx);
  *                 brute_force_seq_n_body (methods.cpp:18-39); across ranks the reaction sums are pushed
  *                 to their owner over NVLink (needs the fused exchange)
  *   "sym_ti"      4 | 8 targets per thread in the FP32 pair-symmetric kernel (0 = auto)
+ *   "sym_itile"   256 | 1024 targets per i-tile of the pair-symmetric pass (0 = auto = 1024; 256 is an
+ *                 experiment for small N on one shard that did not pay off, kept for measurements)
  * Returns NB200_EINVAL for an unknown key. */
 int nb200_set_option(nb200_ctx* ctx, const char* key, long value);
 

@@ -164,7 +164,7 @@ struct Shard {
     int sym_rows_cap = 0;
     std::vector<NbSymRow> sym_rows_host;
     std::vector<int> sym_prefix_host;
-    int sym_key_seg = 0, sym_key_world = 0;
+    int sym_key_seg = 0, sym_key_world = 0, sym_key_tpi = 0;
     double* gacc = nullptr;                           // [3][nalloc]
     unsigned* sym_done = nullptr;                     // [2] push / finish CTA counters
     // fused NVLink exchange (peer stores from the epilogue + flag handshake)
@@ -178,7 +178,10 @@ struct Shard {
 
 constexpr int kMaxWorldP2P = NB_MAX_PEERS + 1;
 constexpr int kSymMaxSlots = kMaxWorldP2P / 2;      // senders of reaction sums per rank: floor(world / 2)
-constexpr size_t kFlagsBytes = 256;                 // 3 * kMaxWorldP2P flag words, padded
+constexpr size_t kFlagsBytes = 256;
+constexpr size_t kSymSmallN = 0;                    // the 256-target i-tile shape is opt-in only ("sym_itile"): measured,
+                                                    // it never beats the 1024 shape or, below N ~ 32768, the ordered pass
+                                                    // (N=16384: 1414 vs 1454 vs 1994 G inter/s: pre-pass + finish launches dominate)                 // 3 * kMaxWorldP2P flag words, padded
 
 }  // namespace
 
@@ -205,7 +208,7 @@ struct nb200_ctx {
     std::vector<unsigned long long> acc_seq_issued;   // per driven shard: pair-symmetric passes with a reaction exchange so far
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
@@ -247,7 +250,11 @@ constexpr int kMaxItile = 1024;
 
 typedef void (*SymKernel)(const NbSymParams);
 // pair-symmetric kernels: FP32 in two register-block shapes (4 targets x 256 threads, 8 x 128), FP64 in one
-SymKernel pick_sym_kernel(int dim, bool f64, int ti) {
+SymKernel pick_sym_kernel(int dim, bool f64, int ti, int block = 0) {
+    if (block == 64) {     // small-N shape: i-tile = one source tile
+        if (f64) return dim == 3 ? nb_force_sym_kernel<3, true, 4, 64> : nb_force_sym_kernel<2, true, 4, 64>;
+        return dim == 3 ? nb_force_sym_kernel<3, false, 4, 64> : nb_force_sym_kernel<2, false, 4, 64>;
+    }
     if (f64) return dim == 3 ? nb_force_sym_kernel<3, true, 4, 256> : nb_force_sym_kernel<2, true, 4, 256>;
     if (dim == 3) return ti == 8 ? nb_force_sym_kernel<3, false, 8, 128> : nb_force_sym_kernel<3, false, 4, 256>;
     return ti == 8 ? nb_force_sym_kernel<2, false, 8, 128> : nb_force_sym_kernel<2, false, 4, 256>;
@@ -293,7 +300,7 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
         CK(cudaMemset(s.suspect, 1, tp));
         {
             // rows: per own i-tile one ordered + one triangular row, plus one row per cross-shard block
-            s.sym_rows_cap = (int)(tp / NB_SYM_ITILE + 1) * (2 + kSymMaxSlots);
+            s.sym_rows_cap = (int)(tp / NB_SYM_ITILE + 1) * (2 + kSymMaxSlots) + 2 * (int)(tp / NB_TILE + 1);
             CK(cudaMalloc(&s.sym_rows, (size_t)s.sym_rows_cap * sizeof(NbSymRow)));
             CK(cudaMalloc(&s.sym_prefix, (size_t)(s.sym_rows_cap + 1) * sizeof(int)));
             CK(cudaMalloc(&s.gacc, 3 * (size_t)ctx->nalloc * sizeof(double)));
@@ -320,6 +327,8 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
     for (int ti = 4; ti <= (ctx->f64 ? 4 : 8); ti += 4)
         CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, ti), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)nb_sym_smem_bytes(D, NB_SYM_ITILE / ti, ctx->f64)));
+    CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, 4, 64), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)nb_sym_smem_bytes(D, 64, ctx->f64)));
     return NB200_OK;
 }
 
@@ -600,8 +609,8 @@ int peer_index(const Shard& s, int rank) {
 
 // The work list of rank g of G (pure host logic, also exported for the CPU tests as
 // nb200_debug_sym_rows): shard g owns source tiles [g*T, (g+1)*T).
-void sym_rows_for(int g, int G, int T, std::vector<NbSymRow>& rows) {
-    const int tpi = NB_SYM_ITILE / NB_TILE;                      // source tiles per i-tile
+void sym_rows_for(int g, int G, int T, std::vector<NbSymRow>& rows, int tpi = NB_SYM_ITILE / NB_TILE) {
+    // tpi = source tiles per i-tile
     const int lo = g * T, hi = (g + 1) * T;
     const int n_it = (T + tpi - 1) / tpi;
     rows.clear();
@@ -631,11 +640,12 @@ void sym_rows_for(int g, int G, int T, std::vector<NbSymRow>& rows) {
     }
 }
 
-int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg, bool cross) {
+int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg, bool cross, int tpi) {
     const int G = cross ? ctx->world : 1;
-    if (!s.sym_rows_host.empty() && s.sym_key_seg == seg && s.sym_key_world == G) return NB200_OK;
+    if (!s.sym_rows_host.empty() && s.sym_key_seg == seg && s.sym_key_world == G && s.sym_key_tpi == tpi) return NB200_OK;
     std::vector<NbSymRow>& rows = s.sym_rows_host;
-    sym_rows_for(cross ? s.rank : 0, G, (int)ctx->tiles_per_shard, rows);
+    sym_rows_for(cross ? s.rank : 0, G, (int)ctx->tiles_per_shard, rows, tpi);
+    s.sym_key_tpi = tpi;
     if ((int)rows.size() > s.sym_rows_cap) return fail(ctx, NB200_ESTATE, "symmetric work list overflow");
     s.sym_prefix_host.assign(rows.size() + 1, 0);
     for (size_t r = 0; r < rows.size(); ++r)
@@ -658,9 +668,13 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     // two register-block shapes of the same 1024-target i-tile: 4 targets x 256 threads, 8 x 128
     // (auto: the 2D chain is shorter, so the per-iteration reduction weighs more: 8 targets per thread there)
     const int want_ti = ctx->opt_sym_ti ? ctx->opt_sym_ti : (D == 2 ? 8 : 4);
-    const int ti = (!ctx->f64 && want_ti == 8) ? 8 : 4;
-    const int block = NB_SYM_ITILE / ti;
-    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, ti);
+    // opt-in shape for small problems on one shard: i-tiles of ONE source tile (4 targets x 64 threads, many
+    // small CTAs); option "sym_itile" = 256 selects it
+    const bool small = !cross && (ctx->opt_sym_itile ? ctx->opt_sym_itile == 256 : ctx->n < kSymSmallN);
+    const int ti = small ? 4 : (!ctx->f64 && want_ti == 8) ? 8 : 4;
+    const int block = small ? 64 : NB_SYM_ITILE / ti;
+    const int itile = ti * block;
+    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, ti, small ? 64 : 0);
     const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64);
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kfn, block, smem));
@@ -669,11 +683,11 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     if (seg <= 0) {
         // this rank evaluates ~ n_it * NT/2 (i-tile, source tile) cells: aim for ~32 units per resident CTA
         // (tail balance) without going under 2 tiles per unit (per-unit start-up) or over 32
-        const long long n_it = (tiles + NB_SYM_ITILE / NB_TILE - 1) / (NB_SYM_ITILE / NB_TILE);
+        const long long n_it = ((long long)tiles * NB_TILE + itile - 1) / itile;
         const long long cells = n_it * (long long)ctx->ntiles / 2;
-        seg = (int)std::max<long long>(2, std::min<long long>(32, cells / (32LL * resident)));
+        seg = (int)std::max<long long>(small ? 1 : 2, std::min<long long>(32, cells / (32LL * resident)));
     }
-    if (int rc = build_sym_rows(ctx, s, seg, cross)) return rc;
+    if (int rc = build_sym_rows(ctx, s, seg, cross, itile / NB_TILE)) return rc;
     NbSymParams Q;
     memset(&Q, 0, sizeof Q);
     Q.src = s.src[cur];
@@ -746,9 +760,9 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     if (&s == &ctx->shards[0]) {
         char buf[320];
         snprintf(buf, sizeof buf,
-                 "%s: fp%d dim=%d n=%zu shards=%d pair-symmetric(TI=%d,block=%d,itile=1024) seg_tiles=%d rows=%d "
+                 "%s: fp%d dim=%d n=%zu shards=%d pair-symmetric(TI=%d,block=%d,itile=%d) seg_tiles=%d rows=%d "
                  "units=%d grid=%d tiles=%lld cutoff=grid-prepass(plain|exact)%s + finish kernel",
-                 mode ? "step" : "forces", ctx->f64 ? 64 : 32, D, ctx->n, ctx->world, ti, block, seg, Q.n_rows, Q.total_units, grid,
+                 mode ? "step" : "forces", ctx->f64 ? 64 : 32, D, ctx->n, ctx->world, ti, block, itile, seg, Q.n_rows, Q.total_units, grid,
                  ctx->ntiles, cross ? " + reaction sums pushed to their owners over NVLink" : "");
         ctx->plan = buf;
     }
@@ -1151,6 +1165,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "detect")) ctx->opt_detect = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "symmetric")) ctx->opt_symmetric = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "sym_ti")) ctx->opt_sym_ti = value == 8 ? 8 : value == 4 ? 4 : 0;
+    else if (!strcmp(key, "sym_itile")) ctx->opt_sym_itile = value == 256 ? 256 : value == 1024 ? 1024 : 0;
     else if (!strcmp(key, "exchange")) {
         if (value == 1 && !ctx->p2p_ready) return fail(ctx, NB200_ESTATE, "peer-store exchange is not attached");
         if (value == 0 && ctx->rank_mode && ctx->world > 1 && !ctx->detached && !ctx->shards[0].comm_nccl)

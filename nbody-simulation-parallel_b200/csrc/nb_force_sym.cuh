@@ -26,7 +26,8 @@
 #pragma once
 #include "nb_force.cuh"
 
-#define NB_SYM_ITILE 1024                           // targets per i-tile = TI * BLOCK = 4 source tiles
+#define NB_SYM_ITILE 1024                           // targets per i-tile (TI * BLOCK) of the large shapes = 4 source tiles;
+                                                    // the small-N shape (4 targets x 64 threads) uses 256 = one source tile
 #define NB_SYM_ROW 14                               // floats per lane row of the transpose scratch (12 used):
                                                     // 14 makes the STS.64 writes and the column reads bank-conflict free
 
@@ -285,11 +286,12 @@ __device__ __forceinline__ void nb_tile_f64_sym(const double* __restrict__ stage
 }
 
 template <int D, bool F64, int TI, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, F64 ? 1 : (BLOCK == 256 ? 2 : 3)) nb_force_sym_kernel(const NbSymParams P) {
+__global__ void __launch_bounds__(BLOCK, BLOCK == 64 ? (F64 ? 4 : 7) : F64 ? 1 : (BLOCK == 256 ? 2 : 3))
+nb_force_sym_kernel(const NbSymParams P) {
     using real = typename NbReal<F64>::type;
     constexpr int NP = D + 1;
-    constexpr int ITILE = NB_SYM_ITILE;
-    static_assert(TI * BLOCK == ITILE, "i-tile is 1024 targets");
+    constexpr int ITILE = TI * BLOCK;
+    static_assert(ITILE % NB_TILE == 0, "an i-tile is a whole number of source tiles");
     constexpr int TILE_ELEMS = NB_TILE * NP;
     constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(real);
     constexpr int NWARPS = BLOCK / 32;

@@ -445,8 +445,10 @@ def test_measured_fp32_peak_is_plausible(pkg):
 # ------------------------------------------------------------------ pair-symmetric pass
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("n", [1, 300, 1024, 5000, 9473])
-@pytest.mark.parametrize("prec,seg_tiles,sym_ti", [(32, 0, 4), (32, 1, 4), (32, 5, 8), (32, 0, 8), (64, 0, 4), (64, 3, 4)])
-def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, prec, seg_tiles, sym_ti):
+@pytest.mark.parametrize("prec,seg_tiles,sym_ti,itile", [(32, 0, 4, 1024), (32, 1, 4, 1024), (32, 5, 8, 1024), (32, 0, 8, 1024),
+                                                         (64, 0, 4, 1024), (64, 3, 4, 1024),
+                                                         (32, 0, 4, 256), (32, 3, 4, 256), (64, 0, 4, 256), (64, 2, 4, 256)])
+def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, prec, seg_tiles, sym_ti, itile):
     """Each unordered pair evaluated once (both reactions) must reproduce the ordered-pair pass and
     the oracle: forces, and a few fused steps through the finish kernel; ragged sizes, duplicates."""
     b = pkg.generators.uniform_cube(n, dim, seed=31 + n)
@@ -456,7 +458,7 @@ def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, prec, seg
     if prec == 32:
         b = pkg.generators.round_to_float(b)
     opts = {"detect": 1, "seg_tiles": seg_tiles}
-    f_sym = pkg.brute_force_cuda_n_body(b, prec, options=dict(opts, symmetric=1, sym_ti=sym_ti))
+    f_sym = pkg.brute_force_cuda_n_body(b, prec, options=dict(opts, symmetric=1, sym_ti=sym_ti, sym_itile=itile))
     f_ord = pkg.brute_force_cuda_n_body(b, prec, options=dict(opts, symmetric=0))
     if prec == 32:
         assert_fp32_parity(pkg, oracle, f_sym, b, f"symmetric n={n}")
@@ -469,9 +471,10 @@ def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, prec, seg
         ctx.set_option("detect", 1)
         ctx.set_option("symmetric", 1)
         ctx.set_option("sym_ti", sym_ti)
+        ctx.set_option("sym_itile", itile)
         ctx.upload(b)
         ctx.forces()
-        assert f"pair-symmetric(TI={sym_ti}" in ctx.plan
+        assert f"pair-symmetric(TI={sym_ti}" in ctx.plan and f"itile={itile}" in ctx.plan
         ctx.step(1e-5, 3)
         got = b.copy()
         ctx.download(got)
