@@ -670,7 +670,7 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     const int want_ti = ctx->opt_sym_ti ? ctx->opt_sym_ti : (D == 2 ? 8 : 4);
     // opt-in shape for small problems on one shard: i-tiles of ONE source tile (4 targets x 64 threads, many
     // small CTAs); option "sym_itile" = 256 selects it
-    const bool small = !cross && (ctx->opt_sym_itile ? ctx->opt_sym_itile == 256 : ctx->n < kSymSmallN);
+    const bool small = !cross && (ctx->opt_sym_itile ? ctx->opt_sym_itile == 256 : (kSymSmallN > 0 && ctx->n < kSymSmallN));
     const int ti = small ? 4 : (!ctx->f64 && want_ti == 8) ? 8 : 4;
     const int block = small ? 64 : NB_SYM_ITILE / ti;
     const int itile = ti * block;
