@@ -312,7 +312,7 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
     {
         // flag words (step, epoch, reaction-sum pass: one per writer rank each) and, behind them in the
         // SAME allocation (one IPC handle), the receive slots of the pair-symmetric pass
-        const size_t slots = (size_t)kSymMaxSlots * 3 * (size_t)ctx->tiles_per_shard * NB_TILE * sizeof(double);
+        const size_t slots = (size_t)(ctx->world / 2) * 3 * (size_t)ctx->tiles_per_shard * NB_TILE * sizeof(double);   // floor(G/2) senders
         CK(cudaMalloc(&s.flags, kFlagsBytes + slots));
         CK(cudaMemset(s.flags, 0, kFlagsBytes));
     }
