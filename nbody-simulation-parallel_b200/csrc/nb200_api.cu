@@ -2,17 +2,20 @@
 // the reference file:line each entry point replaces).
 //
 // One nb200_ctx owns one Shard per device it drives: G shards in a single-process context
-// (nb200_create, ncclCommInitAll), exactly one in a rank context (nb200_create_rank,
-// ncclCommInitRank; one process per GPU under torchrun).  A shard owns a contiguous range of
-// TARGET tiles, their FP64 master state, and a full double-buffered copy of the tile-planar
-// SOURCES of all bodies.  Per step and shard:
-//     compute stream:  pass A (sources = own shard, already local)
-//                      wait(all-gather of this step's positions)
-//                      pass B (sources = the other shards) + fused integrator epilogue
-//                         -> writes the own rows of the NEXT source buffer
-//     comm stream:     wait(pass B) ; in-place ncclAllGather of the next buffer
-// so the all-gather of step k+1 hides behind pass A of step k+1.  NCCL is dlopen'ed on first
-// multi-GPU use (no link-time dependency; a 1-GPU context never touches it).
+// (nb200_create), exactly one in a rank context (nb200_create_rank; one process per GPU under
+// torchrun).  A shard owns a contiguous range of TARGET tiles, their FP64 master state, and a full
+// double-buffered copy of the tile-planar SOURCES of all bodies.
+//
+// Per step and shard, default path (N >= ~32768, fused NVLink exchange attached or one shard):
+//     [wait for the peers' step/epoch flags]  nb_wait_flags_kernel
+//     close-pair pre-pass                      nb_grid_insert/query_kernel
+//     pair-symmetric force pass                nb_force_sym_kernel   (launch_symmetric)
+//     [reaction sums -> their owners' slots]   nb_sym_push_kernel    (peer stores + flag)
+//     epilogue: sum, integrate, new rows to own AND peers' next buffers, step flag   nb_finish_kernel
+// Small N / NCCL exchange / detached shards: the ordered pass nb_force_kernel with the integrator fused
+// into its epilogue; with NCCL, pass A (own sources) overlaps the in-place ncclAllGather of the
+// previous step's rows on the comm stream and pass B takes the other shards' sources.  NCCL is
+// dlopen'ed on first use (no link-time dependency; a 1-GPU context never touches it).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
