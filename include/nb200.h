@@ -134,6 +134,11 @@ int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, do
  * count (or a negative NB200_E* code). */
 int nb200_debug_sym_rows(size_t n, int world, int rank, int* rows_out, int cap);
 
+/* Test aid (pure host logic): the reaction-sum exchange of `rank` in the cross-rank pair-symmetric
+ * pass, 3 ints per partner offset 1..floor(world/2): {rank it pushes to, rank it receives from, slot
+ * index (in the receiver's memory for the push, in its own for the receive)}.  Returns floor(world/2). */
+int nb200_debug_sym_exchange(int world, int rank, int* out, int cap);
+
 /* Measurement aid: the FP32 FMA-pipe throughput this device sustains on independent packed
  * FFMA2 chains (TFLOP/s, 2 flops per lane-op), timed with CUDA events.  It is the denominator of
  * the FP32 roofline fraction bench.py reports next to the nominal SMs x 128 x 2 x clock figure. */

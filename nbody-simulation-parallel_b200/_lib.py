@@ -42,6 +42,7 @@ SIGNATURES = {
     "nb200_accuracy_pct": (_c.c_int, [_ctx_p, _dp, _dp, _dp]),
     "nb200_validation_forces": (_c.c_int, [_ctx_p, _dp, _c.POINTER(_c.c_longlong), _c.c_int]),
     "nb200_measure_fp32_peak": (_c.c_int, [_c.c_int, _dp]),
+    "nb200_debug_sym_exchange": (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_c.c_int), _c.c_int]),
     "nb200_debug_sym_rows": (_c.c_int, [_c.c_size_t, _c.c_int, _c.c_int, _c.POINTER(_c.c_int), _c.c_int]),
     "nb200_last_elapsed_ms": (_c.c_int, [_ctx_p, _dp]),
     "nb200_launch_count": (_c.c_longlong, [_ctx_p]),

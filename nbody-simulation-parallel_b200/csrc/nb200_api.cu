@@ -604,6 +604,11 @@ bool use_symmetric(const nb200_ctx* ctx, bool stepping) {
     return stepping && !ctx->detached && ctx->p2p_ready && ctx->exchange == 1 && ctx->world <= kMaxWorldP2P;
 }
 
+// Reaction-sum exchange of rank g of W at offset off = 1 .. floor(W/2): g pushes the sums on the bodies
+// of rank g+off into slot off-1 of that rank, and finds in its own slot off-1 what rank g-off pushed.
+struct SymExchange { int send_to, recv_from, slot; };
+SymExchange sym_exchange(int g, int W, int off) { return SymExchange{(g + off) % W, (g - off + W) % W, off - 1}; }
+
 int peer_index(const Shard& s, int rank) {
     for (int p = 0; p < s.n_peers; ++p)
         if (s.peer_rank[p] == rank) return p;
@@ -729,16 +734,17 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
         U.done = s.sym_done;
         const size_t slot_doubles = (size_t)3 * tiles * NB_TILE;
         for (int off = 1; off <= n_ex; ++off) {
-            const int h = (s.rank + off) % W, q = (s.rank - off + W) % W;
+            const SymExchange ex = sym_exchange(s.rank, W, off);
+            const int h = ex.send_to, q = ex.recv_from;
             const int ph = peer_index(s, h), pq = peer_index(s, q);
             if (ph < 0 || pq < 0) return fail(ctx, NB200_ESTATE, "peer %d/%d of rank %d is not attached", h, q, s.rank);
             const int k = U.n_dst++;
             U.body_begin[k] = (long long)h * tiles * NB_TILE;
             U.dst_slot[k] = reinterpret_cast<double*>(reinterpret_cast<char*>(s.peer_flags[ph]) + kFlagsBytes) +
-                            (size_t)(off - 1) * slot_doubles;
+                            (size_t)ex.slot * slot_doubles;
             U.dst_flag[k] = s.peer_flags[ph] + 2 * kMaxWorldP2P + s.rank;
             F.slot[F.n_src] = reinterpret_cast<const double*>(reinterpret_cast<const char*>(s.flags) + kFlagsBytes) +
-                              (size_t)(off - 1) * slot_doubles;
+                              (size_t)ex.slot * slot_doubles;
             F.flag[F.n_src] = s.flags + 2 * kMaxWorldP2P + q;
             F.n_src++;
         }
@@ -1503,6 +1509,18 @@ int nb200_debug_sym_rows(size_t n, int world, int rank, int* rows_out, int cap) 
         rows_out[4 * r + 3] = rows[r].flags;
     }
     return (int)rows.size();
+}
+
+int nb200_debug_sym_exchange(int world, int rank, int* out, int cap) {
+    if (world < 1 || rank < 0 || rank >= world || (cap > 0 && !out)) return NB200_EINVAL;
+    const int n_ex = world / 2;
+    for (int off = 1; off <= n_ex && off <= cap; ++off) {
+        const SymExchange ex = sym_exchange(rank, world, off);
+        out[3 * (off - 1) + 0] = ex.send_to;
+        out[3 * (off - 1) + 1] = ex.recv_from;
+        out[3 * (off - 1) + 2] = ex.slot;
+    }
+    return n_ex;
 }
 
 int nb200_measure_fp32_peak(int device, double* tflops) {

@@ -134,3 +134,33 @@ def test_device_generator_mirror_known_answers(pkg):
     rad = np.linalg.norm(p[:, :3], axis=1)
     assert abs(np.median(rad) - 1.3048) < 0.02 and rad.max() < 22.8     # Plummer half-mass radius
     assert not np.array_equal(g.device_bodies(100, 3, 1, seed=1), g.device_bodies(100, 3, 1, seed=2))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8])
+def test_reaction_sum_exchange_is_consistent_across_ranks(pkg, lib, world):
+    """Cross-rank pair-symmetric pass: rank g pushes the reaction sums on rank h's bodies into slot k
+    of h exactly when h expects rank g in its slot k; every rank whose bodies g evaluated as SOURCES
+    (symmetric rows of its work list) receives a push; slots of one receiver never collide."""
+    import ctypes
+    plans = []
+    for rank in range(world):
+        buf = (ctypes.c_int * 24)()
+        k = lib.nb200_debug_sym_exchange(world, rank, buf, 8)
+        assert k == world // 2
+        plans.append([(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(k)])
+    for g, plan in enumerate(plans):
+        for send_to, recv_from, slot in plan:
+            assert send_to != g and recv_from != g and 0 <= slot < world // 2
+            assert (g, slot) in [(rf, sl) for _, rf, sl in plans[send_to]]      # receiver expects g in that slot
+            assert (g, slot) in [(st, sl) for st, _, sl in plans[recv_from]]    # the expected sender targets that slot
+        assert len({sl for _, _, sl in plan}) == len(plan)
+    # every shard a rank touches as symmetric SOURCES is one it pushes to
+    n = 8192 * world
+    T = -(-(-(-n // 256)) // world)
+    for rank in range(world):
+        buf = (ctypes.c_int * (4 * 4096))()
+        nrows = lib.nb200_debug_sym_rows(n, world, rank, buf, 4096)
+        rows = np.frombuffer(buf, dtype=np.int32)[:4 * nrows].reshape(nrows, 4)
+        touched = {int(t0) // T for _, t0, _, fl in rows if fl & 1} | {int(t1 - 1) // T for _, _, t1, fl in rows if fl & 1}
+        touched.discard(rank)
+        assert touched <= {st for st, _, _ in plans[rank]}
