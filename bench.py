@@ -44,7 +44,7 @@ DT = 1e-3
 SEED = 42 + 5
 FLOPS_PER_INTERACTION = 20          # north_star / GPU-Gems convention
 SM_LANES_FP32 = 128                 # FP32 FMA lanes per SM (sm_100)
-CPU_SAMPLE_N = 16384                # bounded CPU sample of the same distribution
+CPU_SAMPLE_N = 65536                # bounded CPU sample of the same distribution (~10-20 s of CPU work in total)
 
 
 def interactions(n: int) -> float:
