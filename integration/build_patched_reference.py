@@ -128,7 +128,6 @@ def main():
     exe = os.path.join(OUT, "nbody_sim")
     subprocess.run(["g++", "-fopenmp", "-o", exe, obj] + ref_objs +
                    [f"-L{libdir}", "-lnb200_methods", "-lnb200", f"-Wl,-rpath,{libdir}"], check=True)
-    shutil.copy(os.path.join(REF, "run_simulations.sh"), os.path.join(OUT, "run_simulations.sh")) if False else None
     print("built", exe)
     return 0
 

@@ -12,7 +12,8 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libnb200.so")
+# NB200_LIB selects an experiment build of the same sources (csrc/Makefile `variant`); never a fallback
+LIB_PATH = os.environ.get("NB200_LIB") or os.path.join(PKG_DIR, "lib", "libnb200.so")
 HEADER = os.path.join(ROOT, "include", "nb200.h")
 
 NB200_FP64, NB200_FP32 = 64, 32

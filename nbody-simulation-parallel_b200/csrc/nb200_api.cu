@@ -181,10 +181,11 @@ struct Shard {
 
 constexpr int kMaxWorldP2P = NB_MAX_PEERS + 1;
 constexpr int kSymMaxSlots = kMaxWorldP2P / 2;      // senders of reaction sums per rank: floor(world / 2)
-constexpr size_t kFlagsBytes = 256;
-constexpr size_t kSymSmallN = 0;                    // the 256-target i-tile shape is opt-in only ("sym_itile"): measured,
-                                                    // it never beats the 1024 shape or, below N ~ 32768, the ordered pass
-                                                    // (N=16384: 1414 vs 1454 vs 1994 G inter/s: pre-pass + finish launches dominate)                 // 3 * kMaxWorldP2P flag words, padded
+constexpr size_t kFlagsBytes = 256;                 // 3 * kMaxWorldP2P flag words, padded
+// The 256-target i-tile shape is opt-in only ("sym_itile" option): measured, it never beats the 1024
+// shape nor, below N ~ 32768, the ordered pass (N=16384: 1414 vs 1454 vs 1994 G inter/s).
+constexpr size_t kSymSmallN = 0;
+constexpr int kSymAlgoDefault = 0;                  // FP32 reaction-sum reduction: 0 transpose, 1 rotation, 2 rotation decoupled
 
 }  // namespace
 
@@ -211,7 +212,7 @@ struct nb200_ctx {
     std::vector<unsigned long long> acc_seq_issued;   // per driven shard: pair-symmetric passes with a reaction exchange so far
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
@@ -253,7 +254,13 @@ constexpr int kMaxItile = 1024;
 
 typedef void (*SymKernel)(const NbSymParams);
 // pair-symmetric kernels: FP32 in two register-block shapes (4 targets x 256 threads, 8 x 128), FP64 in one
-SymKernel pick_sym_kernel(int dim, bool f64, int ti, int block = 0) {
+template <int ALGO> SymKernel pick_sym_kernel_f32(int dim, int ti) {
+    if (dim == 3) return ti == 8 ? nb_force_sym_kernel<3, false, 8, 128, ALGO> : nb_force_sym_kernel<3, false, 4, 256, ALGO>;
+    return ti == 8 ? nb_force_sym_kernel<2, false, 8, 128, ALGO> : nb_force_sym_kernel<2, false, 4, 256, ALGO>;
+}
+SymKernel pick_sym_kernel(int dim, bool f64, int ti, int block = 0, int algo = 0) {
+    if (!f64 && block != 64 && algo == 1) return pick_sym_kernel_f32<1>(dim, ti);
+    if (!f64 && block != 64 && algo == 2) return pick_sym_kernel_f32<2>(dim, ti);
     if (block == 64) {     // small-N shape: i-tile = one source tile
         if (f64) return dim == 3 ? nb_force_sym_kernel<3, true, 4, 64> : nb_force_sym_kernel<2, true, 4, 64>;
         return dim == 3 ? nb_force_sym_kernel<3, false, 4, 64> : nb_force_sym_kernel<2, false, 4, 64>;
@@ -328,8 +335,9 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem_bytes(D, ctx->f64)));
     for (int ti = 4; ti <= (ctx->f64 ? 4 : 8); ti += 4)
-        CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, ti), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)nb_sym_smem_bytes(D, NB_SYM_ITILE / ti, ctx->f64)));
+        for (int algo = 0; algo <= (ctx->f64 ? 0 : 2); ++algo)
+            CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, ti, 0, algo), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)nb_sym_smem_bytes(D, NB_SYM_ITILE / ti, ctx->f64)));
     CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, 4, 64), cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)nb_sym_smem_bytes(D, 64, ctx->f64)));
     return NB200_OK;
@@ -682,7 +690,8 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     const int ti = small ? 4 : (!ctx->f64 && want_ti == 8) ? 8 : 4;
     const int block = small ? 64 : NB_SYM_ITILE / ti;
     const int itile = ti * block;
-    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, ti, small ? 64 : 0);
+    const int algo = (ctx->f64 || small) ? 0 : (ctx->opt_sym_algo >= 0 ? ctx->opt_sym_algo : kSymAlgoDefault);
+    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, ti, small ? 64 : 0, algo);
     const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64);
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kfn, block, smem));
@@ -1174,6 +1183,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "detect")) ctx->opt_detect = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "symmetric")) ctx->opt_symmetric = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "sym_ti")) ctx->opt_sym_ti = value == 8 ? 8 : value == 4 ? 4 : 0;
+    else if (!strcmp(key, "sym_algo")) ctx->opt_sym_algo = (value >= 0 && value <= 2) ? (int)value : -1;
     else if (!strcmp(key, "sym_itile")) ctx->opt_sym_itile = value == 256 ? 256 : value == 1024 ? 1024 : 0;
     else if (!strcmp(key, "exchange")) {
         if (value == 1 && !ctx->p2p_ready) return fail(ctx, NB200_ESTATE, "peer-store exchange is not attached");

@@ -41,6 +41,14 @@ struct NbSymRow {
 };
 #define NB_ROW_SYM 1
 
+// compile-time experiments of the rotation flavour (csrc/Makefile EXTRA=-D...)
+#ifndef NB_ROT_UNROLL
+#define NB_ROT_UNROLL 1
+#endif
+#ifndef NB_ROT_SHFL_ASM
+#define NB_ROT_SHFL_ASM 0
+#endif
+
 struct NbSymParams {
     const void* src;             // tile-planar sources (current step), all bodies (float or double)
     double* gacc;                // [3][gstride] FP64 accumulators indexed by GLOBAL body index
@@ -200,6 +208,111 @@ __device__ __forceinline__ void nb_tile_f32_sym(const float* __restrict__ stage,
     __syncwarp();
 }
 
+// The same tile, reaction sums kept in REGISTERS and rotated through the warp (ALGO 1 / 2).
+// A half tile = 128 sources = 32 "home groups" of four consecutive sources, home group h living in
+// lane h.  In step k lane l works on home group (l + k) & 31: it reads the group's coordinates from
+// the shared-memory stage (one LDS.128 per plane, the lanes hit 32 different 16-byte chunks: conflict
+// free), adds its TI targets' reactions to the group's travelling partial sums and hands those to lane
+// l - 1, which meets the group next (12 SHFL per 8 chains).  After 32 steps every group's sums are
+// back in their home lane, complete for the warp's 128 targets x 128 sources, and leave through one
+// STS.128 per component.  Against the transpose flavour above this drops, per 8 chains, 24 LDS +
+// 7 STS + 18 scalar FADD + the __syncwarp and keeps 12 SHFL.
+//   DECOUPLE = false: the chains accumulate straight onto the travelling sums; each pair of sources
+//                     is shuffled as soon as its TI chains are done, so the other pair's chains cover it
+//   DECOUPLE = true : per-step local sums; sent = received + local (6 FADD2 more per step); what a
+//                     lane receives is first needed a whole step later
+template <int D, int TI, int MODE, bool DECOUPLE>
+__device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ stage, float cutoff,
+                                                    const float (&npos)[TI][3],
+                                                    const float (&mi)[TI],
+                                                    float2 (&a)[TI][3], float* __restrict__ wout, int lane) {
+    const float4* sx = reinterpret_cast<const float4*>(stage);
+    const float4* sy = sx + NB_TILE / 4;
+    const float4* sz = sy + NB_TILE / 4;                      // D == 3 only
+    const float4* sm = sx + D * (NB_TILE / 4);
+#pragma unroll
+    for (int t = 0; t < TI; ++t)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a[t][d] = make_float2(0.f, 0.f);
+    const float inf = __int_as_float(0x7f800000);
+    const int from = (lane + 1) & 31;
+
+#pragma unroll 1
+    for (int hf = 0; hf < NB_TILE / 128; ++hf) {
+        float2 trav[2][3];                                    // sums of the group this lane meets NEXT (or met, see below)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) trav[h][d] = make_float2(0.f, 0.f);
+        NB_UNROLL(NB_ROT_UNROLL)
+        for (int k = 0; k < 32; ++k) {
+            const int q = hf * 32 + ((lane + k) & 31);
+            const float4 X = sx[q], Y = sy[q], M = sm[q];
+            float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (D == 3) Z = sz[q];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float2 xs = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
+                const float2 ys = h ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
+                const float2 zs = h ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
+                const float2 ms = h ? make_float2(M.z, M.w) : make_float2(M.x, M.y);
+                float2 b[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) b[d] = DECOUPLE ? make_float2(0.f, 0.f) : trav[h][d];
+#pragma unroll
+                for (int t = 0; t < TI; ++t) {
+                    const float2 dx = __fadd2_rn(xs, make_float2(npos[t][0], npos[t][0]));
+                    const float2 dy = __fadd2_rn(ys, make_float2(npos[t][1], npos[t][1]));
+                    float2 r2 = __fmul2_rn(dx, dx);
+                    r2 = __ffma2_rn(dy, dy, r2);
+                    float2 dz;
+                    if (D == 3) {
+                        dz = __fadd2_rn(zs, make_float2(npos[t][2], npos[t][2]));
+                        r2 = __ffma2_rn(dz, dz, r2);
+                    }
+                    if (MODE == NB_EXACT) {
+                        r2.x = (r2.x >= cutoff) ? r2.x : inf;
+                        r2.y = (r2.y >= cutoff) ? r2.y : inf;
+                    }
+                    float2 inv;
+                    inv.x = nb_rcp_f32(r2.x);
+                    inv.y = nb_rcp_f32(r2.y);
+                    const float2 w = __fmul2_rn(inv, inv);
+                    const float2 s = __fmul2_rn(w, ms);
+                    const float2 u = __fmul2_rn(w, make_float2(mi[t], mi[t]));
+                    a[t][0] = __ffma2_rn(dx, s, a[t][0]);
+                    b[0] = __ffma2_rn(dx, u, b[0]);
+                    a[t][1] = __ffma2_rn(dy, s, a[t][1]);
+                    b[1] = __ffma2_rn(dy, u, b[1]);
+                    if (D == 3) {
+                        a[t][2] = __ffma2_rn(dz, s, a[t][2]);
+                        b[2] = __ffma2_rn(dz, u, b[2]);
+                    }
+                }
+                // this pair of sources is done for this lane: pass its sums on to lane l - 1
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    float2 v = DECOUPLE ? __fadd2_rn(trav[h][d], b[d]) : b[d];
+#if NB_ROT_SHFL_ASM
+                    // in-place shuffles: the loop-carried pair keeps its registers (no MOVs at the loop end)
+                    asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+f"(v.x) : "r"(from));
+                    asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+f"(v.y) : "r"(from));
+                    trav[h][d] = v;
+#else
+                    trav[h][d].x = __shfl_sync(0xffffffffu, v.x, from);
+                    trav[h][d].y = __shfl_sync(0xffffffffu, v.y, from);
+#endif
+                }
+            }
+        }
+        // after 32 hand-overs the sums of home group `lane` are complete and back in lane `lane`
+        float4* wo = reinterpret_cast<float4*>(wout + hf * 128 + 4 * lane);
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+            wo[d * (NB_TILE / 4)] = make_float4(trav[0][d].x, trav[0][d].y, trav[1][d].x, trav[1][d].y);
+    }
+}
+
 // FP64 flavour: scalar DFMA chains, two sources per iteration, sums kept in FP64 end to end.
 // Per unordered pair 18 DP operations (3 DADD, DMUL + 2 DFMA, 3 DFMA of the reciprocal, DMUL for
 // 1/r^4, 2 DMUL for the two masses, 2 x 3 DFMA) instead of 2 x 14.  The lane rows of the transpose hold
@@ -285,7 +398,8 @@ __device__ __forceinline__ void nb_tile_f64_sym(const double* __restrict__ stage
     __syncwarp();
 }
 
-template <int D, bool F64, int TI, int BLOCK>
+// ALGO (FP32 only): 0 = shared-memory transpose, 1 = register rotation, 2 = register rotation, decoupled
+template <int D, bool F64, int TI, int BLOCK, int ALGO = 0>
 __global__ void __launch_bounds__(BLOCK, BLOCK == 64 ? (F64 ? 4 : 7) : F64 ? 1 : (BLOCK == 256 ? 2 : 3))
 nb_force_sym_kernel(const NbSymParams P) {
     using real = typename NbReal<F64>::type;
@@ -383,11 +497,23 @@ nb_force_sym_kernel(const NbSymParams P) {
             suspect |= P.suspect[it * ITILE + tid + t * BLOCK] != 0;
         }
         const bool warp_suspect = __any_sync(0xffffffffu, suspect) != 0;
-        double accd[TI][3];
+#ifndef NB_ROT_SMEM_ACC
+#define NB_ROT_SMEM_ACC 0
+#endif
+        // FP64 sums of the own targets over the unit: in registers, or (rotation flavours, experiment) in the
+        // shared memory the transpose scratch no longer needs -- 24 registers back for the chains
+        constexpr bool SACC = NB_ROT_SMEM_ACC && !F64 && ALGO != 0;
+        double* sacc = reinterpret_cast<double*>(scr_all) + tid;     // [TI * 3][BLOCK]
+        double accd[SACC ? 1 : TI][3];
+        if constexpr (SACC) {
 #pragma unroll
-        for (int t = 0; t < TI; ++t)
+            for (int k = 0; k < TI * 3; ++k) sacc[k * BLOCK] = 0.0;
+        } else {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) accd[t][d] = 0.0;
+            for (int t = 0; t < TI; ++t)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) accd[t][d] = 0.0;
+        }
 
         for (int t = 0; t < ntl; ++t) {
             if (tid == 0 && t + NB_STAGES - 1 < ntl) {
@@ -410,6 +536,7 @@ nb_force_sym_kernel(const NbSymParams P) {
                 for (int tt = 0; tt < TI; ++tt) exact_tile |= (ts + t == own_tile[tt]);
             }
             if constexpr (F64) {
+                static_assert(!SACC, "smem accumulators are an FP32 experiment");
                 const double* dstage = reinterpret_cast<const double*>(stage);
                 const double(&pos)[TI][3] = reinterpret_cast<const double(&)[TI][3]>(tq);
                 const double(&mid)[TI] = reinterpret_cast<const double(&)[TI]>(mi);
@@ -430,8 +557,13 @@ nb_force_sym_kernel(const NbSymParams P) {
                 float2 a[TI][3];
                 if (sym) {
                     float* fwout = reinterpret_cast<float*>(wout);
-                    if (exact_tile) nb_tile_f32_sym<D, TI, NB_EXACT>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
-                    else nb_tile_f32_sym<D, TI, NB_PLAIN>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
+                    if constexpr (ALGO == 0) {
+                        if (exact_tile) nb_tile_f32_sym<D, TI, NB_EXACT>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
+                        else nb_tile_f32_sym<D, TI, NB_PLAIN>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
+                    } else {
+                        if (exact_tile) nb_tile_f32_sym_rot<D, TI, NB_EXACT, ALGO == 2>(fstage, cutoff_f, npos, mif, a, fwout, lane);
+                        else nb_tile_f32_sym_rot<D, TI, NB_PLAIN, ALGO == 2>(fstage, cutoff_f, npos, mif, a, fwout, lane);
+                    }
                 } else {
                     if (exact_tile) nb_tile_f32<D, TI, 1, NB_EXACT, 1>(fstage, 0, cutoff_f, npos, a);
                     else nb_tile_f32<D, TI, 1, NB_PLAIN, 1>(fstage, 0, cutoff_f, npos, a);
@@ -439,7 +571,10 @@ nb_force_sym_kernel(const NbSymParams P) {
 #pragma unroll
                 for (int tt = 0; tt < TI; ++tt)
 #pragma unroll
-                    for (int d = 0; d < D; ++d) accd[tt][d] += (double)(a[tt][d].x + a[tt][d].y);
+                    for (int d = 0; d < D; ++d) {
+                        if constexpr (SACC) sacc[(tt * 3 + d) * BLOCK] += (double)(a[tt][d].x + a[tt][d].y);
+                        else accd[tt][d] += (double)(a[tt][d].x + a[tt][d].y);
+                    }
             }
             __syncwarp();
             if (lane == 0) nb_mbar_arrive(&empty_bar[slot]);
@@ -469,7 +604,8 @@ nb_force_sym_kernel(const NbSymParams P) {
             for (int d = 0; d < D; ++d) {
                 const int li = it * ITILE + tid + t * BLOCK;
                 if (li < P.own_count)
-                    atomicAdd(&P.gacc[(size_t)d * P.gstride + (size_t)P.tgt_base + li], accd[t][d]);
+                    atomicAdd(&P.gacc[(size_t)d * P.gstride + (size_t)P.tgt_base + li],
+                              SACC ? sacc[(t * 3 + d) * BLOCK] : accd[SACC ? 0 : t][d]);
             }
     }
 

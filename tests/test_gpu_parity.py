@@ -483,6 +483,27 @@ def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, prec, seg
     assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= (2e-6 if prec == 32 else 1e-12) * scale
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("n", [300, 5000, 9473])
+@pytest.mark.parametrize("algo,sym_ti,seg_tiles", [(1, 4, 0), (1, 8, 3), (2, 4, 1), (2, 8, 0), (0, 4, 0)])
+def test_pair_symmetric_reduction_flavours(pkg, oracle, dim, n, algo, sym_ti, seg_tiles):
+    """The three ways the FP32 pair-symmetric kernel sums the reactions on the streamed sources
+    (sym_algo 0: shared-memory transpose, 1: register rotation through the warp, 2: rotation with
+    decoupled hand-over) must all reproduce the oracle: forces and a few fused steps; ragged sizes,
+    a duplicate and a pair under the cut-off included."""
+    b = pkg.generators.uniform_cube(n, dim, seed=77 + n)
+    b[17, :dim] = b[3, :dim]
+    b[101, :dim] = b[100, :dim] + 2e-6
+    b = pkg.generators.round_to_float(b)
+    opts = {"detect": 1, "symmetric": 1, "sym_algo": algo, "sym_ti": sym_ti, "seg_tiles": seg_tiles}
+    f = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32, options=opts)
+    assert_fp32_parity(pkg, oracle, f, b, f"sym_algo={algo} TI={sym_ti} n={n}")
+    got = pkg.brute_force_cuda_simulate(b, 1e-5, 3, pkg.NB200_FP32, options=opts)
+    want = pkg.brute_force_cuda_simulate(b, 1e-5, 3, pkg.NB200_FP32, options={"detect": 1, "symmetric": 0})
+    scale = np.abs(want[:, :2 * dim]).max()
+    assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= 2e-6 * scale
+
+
 # ------------------------------------------------------------------ -a 1 column and validation print on the device
 @pytest.mark.parametrize("dim,n", [(3, 3001), (2, 1000), (3, 5)])
 def test_device_side_accuracy_and_validation_forces(pkg, oracle, dim, n):
