@@ -32,7 +32,9 @@ import time
 
 import numpy as np
 
-os.environ["NCCL_DEBUG"] = "WARN"   # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner off it
+# rank 0 prints exactly ONE JSON line on stdout.  Without a caller-set NCCL_DEBUG keep NCCL quiet; a caller that
+# asks for INFO (the driver's communicator check) gets it untouched.
+os.environ.setdefault("NCCL_DEBUG", "WARN")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -42,6 +44,16 @@ N_DEFAULT = 1 << 20
 DIM = 3
 DT = 1e-3
 SEED = 42 + 5
+# BASELINE.json configs (SURVEY 8d inputs: seeded, uniform cube / Plummer).  dt: the reference defines none
+# (SURVEY F4); c2/c3 use a step that resolves the closest pairs of the uniform sets so that the 100-step
+# energy drift is a statement about the integrator, not about two bodies flung apart in one step.
+CONFIGS = {
+    "c2": {"dim": 3, "n": 16384, "dist": "cube", "steps": 100, "dt": 1e-4, "seed": 44},
+    "c3": {"dim": 2, "n": 65536, "dist": "cube", "steps": 100, "dt": 1e-5, "seed": 45},
+    "c4": {"dim": 3, "n": 262144, "dist": "plummer", "steps": 100, "dt": 1e-3, "seed": 46},
+    "c5": {"dim": 3, "n": N_DEFAULT, "dist": "cube", "steps": 10, "dt": DT, "seed": SEED},
+}
+PARITY_TARGETS = 1024
 FLOPS_PER_INTERACTION = 20          # north_star / GPU-Gems convention
 SM_LANES_FP32 = 128                 # FP32 FMA lanes per SM (sm_100)
 CPU_SAMPLE_N = 65536                # bounded CPU sample of the same distribution (~10-20 s of CPU work in total)
@@ -102,16 +114,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------- CPU legs
-def cpu_reference_leg(n_sample: int, repeats: int = 1) -> dict:
+def cpu_reference_leg(n_sample: int, dim: int = DIM, cfg: dict | None = None, repeats: int = 1) -> dict:
     """Time the reference's own brute-force variants (oracle/_ref; else the oracle port) on this
     box's host cores, one force evaluation each (the reference's convention, utils.h:87-104)."""
     oracle = entry.load_oracle()
     pkg = entry.load_package()
-    bodies = pkg.generators.uniform_cube(N_DEFAULT, DIM, seed=SEED)[:n_sample].copy()
+    cfg = cfg or CONFIGS["c5"]
+    bodies = make_bodies(pkg.generators, cfg)[:n_sample].copy()
     inter = interactions(n_sample)
     cores = os.cpu_count() or 1
     out = {"unit": "G interactions/s", "cores": cores,
-           "sample": f"first {n_sample} bodies of the 3D uniform-cube workload, one force evaluation per variant"}
+           "sample": f"first {n_sample} bodies of the {dim}D {cfg['dist']} workload, one force evaluation per variant"}
     if oracle.have_ref():
         out["kind"] = "reference"
         thr = oracle.ref_threads()
@@ -145,8 +158,13 @@ def run_reference_arm(args) -> None:
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     oracle = entry.load_oracle()
     pkg = entry.load_package()
+    cfg = dict(CONFIGS[args.config])
+    if args.n:
+        cfg["n"] = args.n
+    args.n = cfg["n"]
+    DIM, DT = cfg["dim"], cfg["dt"]
     n_s = min(args.n, CPU_SAMPLE_N)
-    bodies = pkg.generators.uniform_cube(args.n, DIM, seed=SEED)[:n_s].copy()
+    bodies = make_bodies(pkg.generators, cfg)[:n_s].copy()
     use_ref = oracle.have_ref()
     # the reference arm gets the reference's FASTEST brute-force variant on this host
     variant = "omp_2"
@@ -167,11 +185,11 @@ def run_reference_arm(args) -> None:
     val = interactions(n_s) * args.steps / dt / 1e9
     cores = (oracle.ref_threads()["omp"] if use_ref else oracle.num_threads())
     line = {
-        "impl": "reference", "metric": "G body-body interactions/s (brute-force step, 3D)", "value": round(val, 4),
+        "impl": "reference", "metric": f"G body-body interactions/s (brute-force step, {DIM}D)", "value": round(val, 4),
         "unit": "G interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"c5: brute-force 3D uniform cube, N={args.n} (reference arm: CPU sample of {n_s} bodies)",
+        "config": {"workload": f"{args.config}: brute-force {DIM}D {cfg['dist']}, N={args.n} (reference arm: CPU sample of {n_s} bodies)",
                    "n": args.n, "dim": DIM, "dt": DT},
         "cpu_baseline": {"value": round(val, 4), "unit": "G interactions/s", "cores": cores,
                          "kind": "reference" if use_ref else "port",
@@ -227,6 +245,138 @@ def shared_pinned_bodies(bodies, rank, world, torch, barrier):
     return mm, release
 
 
+# ------------------------------------------------------------------------------------- parity gate
+def make_bodies(gen, cfg):
+    if cfg["dist"] == "plummer":
+        return gen.plummer(cfg["n"], seed=cfg["seed"])
+    return gen.uniform_cube(cfg["n"], cfg["dim"], seed=cfg["seed"])
+
+
+def band_ok(err, kappa, prec):
+    """The parity criterion of tests/test_gpu_parity.py on a set of (sampled) bodies."""
+    if prec == 64:
+        return bool(err.max() <= 1e-12)
+    bound = np.maximum(1e-5, 2.5e-7 * kappa)
+    return bool(np.all(err <= bound) and np.percentile(err, 99) <= 1e-5)
+
+
+def parity_gate(pkg, oracle, D, ctx, bodies, dim, prec, dt, rank, world, local, bcast_ok):
+    """After the timed region: a fresh force evaluation and ONE fused step of the context that was timed
+    (same library, same launch path, all ranks), checked on PARITY_TARGETS sampled targets against the
+    CPU oracle (checker only) and, for N > 1 GPUs, against a 1-GPU context of the same library on rank 0.
+    The step is checked through the forces it implies: F = m (v1 - v0) / dt, and x1 = x0 + v1 dt."""
+    gen = pkg.generators
+    n = bodies.shape[0]
+    src = gen.round_to_float(bodies) if prec == 32 else bodies
+    lo, hi = ctx.shard_range()
+    ctx.upload(src)
+    f = np.zeros((n, dim))
+    ctx.forces(out=f)
+    ctx.step(dt, 1)
+    after = src.copy()
+    ctx.download(after)
+    if world > 1:
+        f = D.assemble_rows(f, lo, hi)
+        after = D.assemble_rows(after, lo, hi)
+    out = None
+    if rank == 0:
+        idx = np.sort(np.random.default_rng(2024).choice(n, min(PARITY_TARGETS, n), replace=False))
+        ref = oracle.forces_targets(src, idx)
+        kappa = oracle.condition_targets(src, idx) if prec == 32 else np.ones(idx.size)
+        m = src[idx, 2 * dim:2 * dim + 1]
+        implied = (after[idx, dim:2 * dim] - src[idx, dim:2 * dim]) * m / dt
+        e_f = gen.relative_norm_error(f[idx], ref)
+        e_s = gen.relative_norm_error(implied, ref)
+        # the step's forces are read back through v1 - v0: allow for that cancellation in FP64
+        cancel = np.abs(src[idx, dim:2 * dim]).max(axis=1) / np.maximum(np.abs(after[idx, dim:2 * dim] - src[idx, dim:2 * dim]).max(axis=1), 1e-300)
+        e_s_adj = np.maximum(e_s - 4.5e-16 * cancel, 0.0)
+        x_res = np.abs(after[:, :dim] - (src[:, :dim] + after[:, dim:2 * dim] * dt)).max() / np.abs(src[:, :dim]).max()
+        ok = band_ok(e_f, kappa, prec) and band_ok(e_s_adj, kappa, prec) and x_res <= 4e-16
+        out = {"targets": int(idx.size), "forces_max_rel_err": float(e_f.max()), "forces_p99": float(np.percentile(e_f, 99)),
+               "step_max_rel_err": float(e_s_adj.max()), "step_p99": float(np.percentile(e_s_adj, 99)),
+               "position_update_residual": float(x_res),
+               "tol": ("max <= 1e-12 vs the CPU oracle" if prec == 64 else
+                       "per body <= max(1e-5, 2.5e-7*kappa) and p99 <= 1e-5 vs the CPU oracle on the float-quantised inputs"),
+               "kappa_max": float(kappa.max()) if prec == 32 else None}
+        if world > 1:
+            with pkg.NBodyCuda(dim, n, prec) as one:
+                one.upload(src)
+                f1 = one.forces()
+                one.step(dt, 1)
+                a1 = src.copy()
+                one.download(a1)
+            scale = np.abs(a1[:, :2 * dim]).max()
+            dx = float(np.abs(after[:, :2 * dim] - a1[:, :2 * dim]).max() / scale)
+            df = gen.relative_norm_error(f, f1)
+            tol_x = 1e-12 if prec == 64 else 1e-6
+            out["vs_1gpu"] = {"bodies": n, "state_max_diff_rel": dx, "forces_max_rel_diff": float(df.max()),
+                              "forces_p99_rel_diff": float(np.percentile(df, 99)), "tol_state": tol_x}
+            ok = ok and dx <= tol_x and (df.max() <= 1e-12 if prec == 64 else np.percentile(df, 99) <= 1e-5)
+        out["ok"] = bool(ok)
+    ok_all = bcast_ok(out["ok"] if out else True)
+    return out, ok_all
+
+
+def energy_of(ctx):
+    ke, pe = ctx.energy()
+    return ke + pe
+
+
+def run_config(pkg, oracle, name, prec_list=(32, 64)):
+    """One BASELINE config on ONE GPU: throughput of a single nb200_step(nsteps) call, sampled-target parity
+    at the initial positions, relative energy drift over the run for FP32 and FP64."""
+    cfg = CONFIGS[name]
+    gen = pkg.generators
+    dim, n = cfg["dim"], cfg["n"]
+    bodies = make_bodies(gen, cfg)
+    idx = np.sort(np.random.default_rng(7).choice(n, min(PARITY_TARGETS, n), replace=False))
+    res = {"workload": f"{name}: brute-force {dim}D N={n} {cfg['dist']}, {cfg['steps']} steps, dt={cfg['dt']}"}
+    for prec in prec_list:
+        src = gen.round_to_float(bodies) if prec == 32 else bodies
+        with pkg.NBodyCuda(dim, n, prec) as ctx:
+            ctx.upload(src)
+            f = ctx.forces()
+            ref = oracle.forces_targets(src, idx)
+            err = gen.relative_norm_error(f[idx], ref)
+            kappa = oracle.condition_targets(src, idx) if prec == 32 else np.ones(idx.size)
+            e0 = energy_of(ctx)
+            ctx.step(cfg["dt"], 3)                      # warm-up steps (part of the trajectory)
+            ctx.step(cfg["dt"], cfg["steps"] - 3)
+            ms = ctx.last_elapsed_ms / (cfg["steps"] - 3)
+            e1 = energy_of(ctx)
+            res[f"f{prec}"] = {
+                "value": round(n * (n - 1.0) / ms / 1e6, 1), "unit": "G interactions/s", "ms_per_step": round(ms, 4),
+                "parity": {"targets": int(idx.size), "max_rel_err": float(err.max()), "p99": float(np.percentile(err, 99)),
+                           "ok": band_ok(err, kappa, prec)},
+                "energy_drift": float((e1 - e0) / e0), "plan": ctx.plan.split(" cutoff=")[0]}
+    if "f32" in res and "f64" in res:
+        d32, d64 = res["f32"]["energy_drift"], res["f64"]["energy_drift"]
+        res["energy_drift_fp32_minus_fp64"] = d32 - d64
+        res["ok"] = bool(res["f32"]["parity"]["ok"] and res["f64"]["parity"]["ok"] and
+                         abs(d32 - d64) <= 1e-5 + 1e-2 * abs(d64))
+    return res
+
+
+def fp32_population_error(pkg, bodies, dim):
+    """FP32-mode forces of ALL bodies against FP64 contexts on the device (nb200_compare_forces): (a) the same
+    float-quantised inputs -- the arithmetic error the FP32 contract is stated on -- and (b) the unrounded
+    inputs -- what the 24-bit quantisation of the positions adds."""
+    gen = pkg.generators
+    n = bodies.shape[0]
+    rb = gen.round_to_float(bodies)
+    out = {}
+    with pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as c32:
+        c32.upload(bodies)
+        c32.forces()
+        for key, src in (("vs_fp64_same_quantised_inputs", rb), ("vs_fp64_unrounded_inputs", bodies)):
+            with pkg.NBodyCuda(dim, n, pkg.NB200_FP64) as c64:
+                c64.upload(src)
+                c64.forces()
+                st = c32.compare_forces(c64)
+            out[key] = {k: st[k] for k in ("bodies", "max", "over_1e-5", "over_1e-4", "over_1e-3", "nonfinite", "histogram")}
+    return out
+
+
 # ------------------------------------------------------------------------------------- product arm
 def run_product_arm(args) -> None:
     import torch
@@ -257,8 +407,20 @@ def run_product_arm(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    n, prec = args.n, args.precision
-    bodies = pkg.generators.uniform_cube(n, DIM, seed=SEED)
+    cfg = dict(CONFIGS[args.config])
+    if args.n:
+        cfg["n"] = args.n
+    n, prec, DIM, DT = cfg["n"], args.precision, cfg["dim"], cfg["dt"]
+    bodies = make_bodies(pkg.generators, cfg)
+    oracle = entry.load_oracle() if (rank == 0 and not args.no_parity) else None    # checker only, after the timed region
+
+    def bcast_ok(flag: bool) -> bool:
+        if world == 1:
+            return flag
+        t = torch.tensor([1 if flag else 0], device="cuda")
+        dist.broadcast(t, src=0)
+        return bool(int(t.item()))
+
     if world > 1:
         ctx = D.create_rank_context(pkg, DIM, n, prec, device=local)
     else:
@@ -323,6 +485,11 @@ def run_product_arm(args) -> None:
     d2h = (hi - lo) * (2 * DIM + 1) * 8
     release_host()
 
+    # ---- parity gate on the context that was just timed (every rank takes part; the oracle runs on rank 0)
+    parity, parity_ok = (None, True)
+    if not args.no_parity:
+        parity, parity_ok = parity_gate(pkg, oracle, D, ctx, bodies, DIM, prec, DT, rank, world, local, bcast_ok)
+
     # ---- FP64 flavour of the same step (the reference's own precision), short
     fp64 = None
     if prec == 32 and not args.no_fp64:
@@ -336,12 +503,26 @@ def run_product_arm(args) -> None:
         v64 = interactions(n) * 2 / (ms64 * 1e-3) / 1e9
         fp64 = {"value": round(v64, 2), "unit": "G interactions/s", "ms_per_step": round(ms64 / 2, 3), "steps": 2,
                 "roofline_frac_fp64": round(v64 * 1e9 * FLOPS_PER_INTERACTION / (148 * 64 * 2 * 1.965e9 * world), 4)}
+        if not args.no_parity:
+            p64, ok64 = parity_gate(pkg, oracle, D, ctx, bodies, DIM, pkg.NB200_FP64, DT, rank, world, local, bcast_ok)
+            parity_ok = parity_ok and ok64
+            if p64 is not None:
+                fp64["parity"] = p64
     ctx.close()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if not parity_ok:
+            sys.exit(3)
         return
+
+    # ---- the other BASELINE configs and the full-population FP32 error, 1 GPU only (short)
+    sub_results, population = None, None
+    if world == 1 and args.config == "c5" and not args.n and not args.no_sub:
+        sub_results = {name: run_config(pkg, oracle or entry.load_oracle(), name) for name in ("c2", "c3", "c4")}
+        if prec == 32:
+            population = fp32_population_error(pkg, bodies, DIM)
 
     props = torch.cuda.get_device_properties(local)
     sms = props.multi_processor_count
@@ -373,15 +554,18 @@ def run_product_arm(args) -> None:
         "hbm_algorithmic_bytes_per_step": n * (16 if prec == 32 else 32) + n * (2 * DIM * 8 * 2 + 8 + 3 * 8 * 2),
     }
     line = {
-        "metric": "G body-body interactions/s (brute-force step, 3D)", "value": round(value, 2),
+        "metric": f"G body-body interactions/s (brute-force step, {DIM}D)", "value": round(value, 2),
         "unit": "G interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32" if prec == 32 else "f64", "data": "synthetic",
-        "config": {"workload": f"c5: brute-force 3D uniform cube, N={n}, fused force+integrate step, dt={DT}",
+        "config": {"workload": f"{args.config}: brute-force {DIM}D {cfg['dist']}, N={n}, fused force+integrate step, dt={DT}",
                    "n": n, "dim": DIM, "precision": prec,
                    "parallelism": (f"targets sharded over {world} GPU(s); each block of pairs evaluated by one of its two "
                                    "ranks, reaction sums and new positions stored into the peers' buffers over NVLink"
                                    if world > 1 else "1 GPU"),
+                   "collective": ("none on the data path: peer stores over CUDA-IPC-mapped NVLink memory issued by the force/finish "
+                                  "kernels + flag words; torch.distributed (NCCL) only bootstraps, barriers and reduces the timing"
+                                  if world > 1 else "none"),
                    "l2": "flushed between timed steps (256 MiB write)", "plan": plan},
         "pipelined": {"value": round(pipelined, 2), "ms_per_step": round(pipe_ms / args.steps, 3),
                       "note": "same K steps in one nb200_step call, no L2 flush"},
@@ -392,13 +576,22 @@ def run_product_arm(args) -> None:
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    if parity is not None:
+        line["parity"] = parity
     if fp64:
         line["fp64"] = fp64
+    if sub_results:
+        line["sub_results"] = sub_results
+    if population:
+        line["fp32_error_all_bodies"] = population
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_reference_leg(min(n, CPU_SAMPLE_N))
+        line["cpu_baseline"] = cpu_reference_leg(min(n, CPU_SAMPLE_N), DIM, cfg)
     if world > 1:
         dist.destroy_process_group()
     print(json.dumps(line), flush=True)
+    if not parity_ok or (sub_results and not all(r.get("ok", True) for r in sub_results.values())):
+        print("bench.py: PARITY GATE FAILED (see the 'parity' / 'sub_results' objects of the line above)", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -407,7 +600,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nb200", choices=["nb200", "reference"])
-    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--config", default="c5", choices=sorted(CONFIGS), help="BASELINE.json config timed as the headline (default c5)")
+    ap.add_argument("--n", type=int, default=0, help="override the config's body count")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate after the timed region")
+    ap.add_argument("--no-sub", action="store_true", help="skip the c2/c3/c4 sub-results and the full-population FP32 error")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--opt", action="append", help="libnb200 option key=value (e.g. variant=1)")
     ap.add_argument("--no-cpu", action="store_true")

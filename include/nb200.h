@@ -151,6 +151,17 @@ int nb200_measure_fp32_peak(int device, double* tflops);
  * download).  Rank contexts count their own rows only: the per-rank values add up to the total. */
 int nb200_accuracy_pct(nb200_ctx* ctx, const double* forces, const double* reference, double* pct);
 
+/* Full-population parity metric on the device: per-body norm-wise relative difference
+ * ||F_a - F_b|| / ||F_b|| between the forces of the last nb200_forces call of two contexts over the
+ * same n bodies (same dim, same shard layout and devices), e.g. an NB200_FP32 context against an
+ * NB200_FP64 one -- the measurement compute_accuracy_omp's 1 % criterion (utils.h:170-219) is too
+ * coarse for.  stats_out = NB200_COMPARE_STATS doubles:
+ *   [0] bodies compared  [1] maximum difference  [2] body index of the maximum  [3] non-finite count
+ *   [4 + k], k = 0..17: bodies with difference in [10^(k-17), 10^(k-16)) (k = 0: everything below 1e-16)
+ * Rank contexts compare their own rows; counts add up over ranks, the maximum is the max. */
+#define NB200_COMPARE_STATS 22
+int nb200_compare_forces(nb200_ctx* a, nb200_ctx* b, double* stats_out);
+
 /* print_validation_forces<D> (utils.h:138-151) without downloading all forces: the forces of the
  * bodies the reference prints (0-based i with (i+1) % (n/3) == 0) from the last nb200_forces
  * call.  forces_out = cap*D doubles, index_out = cap body indices; returns the number of bodies

@@ -152,6 +152,17 @@ class NBodyCuda:
                     "accuracy_pct")
         return pct.value
 
+    def compare_forces(self, other: "NBodyCuda") -> dict:
+        """Per-body norm-wise relative difference between this context's resident forces and ``other``'s
+        (the reference side), over ALL bodies, on the device (nb200_compare_forces)."""
+        st = (ctypes.c_double * _lib.COMPARE_STATS)()
+        self._check(self._lib.nb200_compare_forces(self._h, other._h, st), "compare_forces")
+        hist = [int(v) for v in st[4:]]
+        edges = [f"<1e-16"] + [f"1e{k - 17}..1e{k - 16}" for k in range(1, 18)]
+        return {"bodies": int(st[0]), "max": float(st[1]), "argmax": int(st[2]), "nonfinite": int(st[3]),
+                "histogram": {e: c for e, c in zip(edges, hist) if c},
+                "over_1e-5": int(sum(hist[12:])), "over_1e-4": int(sum(hist[13:])), "over_1e-3": int(sum(hist[14:]))}
+
     def validation_forces(self, cap: int = 8) -> tuple[np.ndarray, np.ndarray]:
         """The (index, force) rows print_validation_forces (utils.h:138-151) would print."""
         out = np.zeros((cap, self.dim))

@@ -19,6 +19,7 @@ HEADER = os.path.join(ROOT, "include", "nb200.h")
 NB200_FP64, NB200_FP32 = 64, 32
 UNIQUE_ID_BYTES = 128
 IPC_BYTES = 256
+COMPARE_STATS = 22
 
 _c = ctypes
 _ctx_p = _c.c_void_p
@@ -41,6 +42,7 @@ SIGNATURES = {
     "nb200_step": (_c.c_int, [_ctx_p, _c.c_double, _c.c_double, _c.c_double, _c.c_int]),
     "nb200_energy": (_c.c_int, [_ctx_p, _c.c_double, _c.c_double, _dp, _dp]),
     "nb200_accuracy_pct": (_c.c_int, [_ctx_p, _dp, _dp, _dp]),
+    "nb200_compare_forces": (_c.c_int, [_ctx_p, _ctx_p, _dp]),
     "nb200_validation_forces": (_c.c_int, [_ctx_p, _dp, _c.POINTER(_c.c_longlong), _c.c_int]),
     "nb200_measure_fp32_peak": (_c.c_int, [_c.c_int, _dp]),
     "nb200_debug_sym_exchange": (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_c.c_int), _c.c_int]),

@@ -185,7 +185,12 @@ constexpr size_t kFlagsBytes = 256;                 // 3 * kMaxWorldP2P flag wor
 // The 256-target i-tile shape is opt-in only ("sym_itile" option): measured, it never beats the 1024
 // shape nor, below N ~ 32768, the ordered pass (N=16384: 1414 vs 1454 vs 1994 G inter/s).
 constexpr size_t kSymSmallN = 0;
-constexpr int kSymAlgoDefault = 0;                  // FP32 reaction-sum reduction: 0 transpose, 1 rotation, 2 rotation decoupled
+// Reaction-sum reduction of the pair-symmetric kernel: 0 shared-memory transpose, 1 register rotation through the
+// warp, 2 (FP32) rotation with decoupled hand-over.  Measured at N = 2^20, FP32 3D: 3323 / 3811 / 3757 G inter/s
+// with 4 x 256 threads, 3864 with 8 x 128 and rotation (profiles/r02_sym_variants.jsonl).
+constexpr int kSymAlgoDefault = 1;
+constexpr int kSymTiF32 = 8;
+constexpr int kSymTiF64 = 4;
 
 }  // namespace
 
@@ -212,7 +217,7 @@ struct nb200_ctx {
     std::vector<unsigned long long> acc_seq_issued;   // per driven shard: pair-symmetric passes with a reaction exchange so far
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
@@ -253,22 +258,31 @@ int fail(nb200_ctx* c, int code, const char* fmt, ...) {
 constexpr int kMaxItile = 1024;
 
 typedef void (*SymKernel)(const NbSymParams);
-// pair-symmetric kernels: FP32 in two register-block shapes (4 targets x 256 threads, 8 x 128), FP64 in one
-template <int ALGO> SymKernel pick_sym_kernel_f32(int dim, int ti) {
-    if (dim == 3) return ti == 8 ? nb_force_sym_kernel<3, false, 8, 128, ALGO> : nb_force_sym_kernel<3, false, 4, 256, ALGO>;
-    return ti == 8 ? nb_force_sym_kernel<2, false, 8, 128, ALGO> : nb_force_sym_kernel<2, false, 4, 256, ALGO>;
-}
-SymKernel pick_sym_kernel(int dim, bool f64, int ti, int block = 0, int algo = 0) {
-    if (!f64 && block != 64 && algo == 1) return pick_sym_kernel_f32<1>(dim, ti);
-    if (!f64 && block != 64 && algo == 2) return pick_sym_kernel_f32<2>(dim, ti);
-    if (block == 64) {     // small-N shape: i-tile = one source tile
-        if (f64) return dim == 3 ? nb_force_sym_kernel<3, true, 4, 64> : nb_force_sym_kernel<2, true, 4, 64>;
-        return dim == 3 ? nb_force_sym_kernel<3, false, 4, 64> : nb_force_sym_kernel<2, false, 4, 64>;
+// pair-symmetric kernels (nb_force_sym.cuh)
+// One shape of the pair-symmetric kernel: targets per thread x threads (i-tile = ti * block targets).
+struct SymShape { int ti, block; };
+template <int D, bool F64, int ALGO> SymKernel sym_kernel_of(SymShape sh) {
+    if (sh.block == 64) return nb_force_sym_kernel<D, F64, 4, 64, 0>;            // small-N experiment, transpose only
+    if constexpr (F64) {
+        if (sh.ti == 2) return sh.block == 128 ? nb_force_sym_kernel<D, true, 2, 128, ALGO> : nb_force_sym_kernel<D, true, 2, 256, ALGO>;
+        return nb_force_sym_kernel<D, true, 4, 256, ALGO>;
+    } else {
+        if (sh.ti == 8) return nb_force_sym_kernel<D, false, 8, 128, ALGO>;
+        return sh.block == 128 ? nb_force_sym_kernel<D, false, 4, 128, ALGO> : nb_force_sym_kernel<D, false, 4, 256, ALGO>;
     }
-    if (f64) return dim == 3 ? nb_force_sym_kernel<3, true, 4, 256> : nb_force_sym_kernel<2, true, 4, 256>;
-    if (dim == 3) return ti == 8 ? nb_force_sym_kernel<3, false, 8, 128> : nb_force_sym_kernel<3, false, 4, 256>;
-    return ti == 8 ? nb_force_sym_kernel<2, false, 8, 128> : nb_force_sym_kernel<2, false, 4, 256>;
 }
+template <int D, bool F64> SymKernel sym_kernel_of(SymShape sh, int algo) {
+    if (algo == 1) return sym_kernel_of<D, F64, 1>(sh);
+    if constexpr (!F64) { if (algo == 2) return sym_kernel_of<D, false, 2>(sh); }
+    return sym_kernel_of<D, F64, 0>(sh);
+}
+SymKernel pick_sym_kernel(int dim, bool f64, SymShape sh, int algo) {
+    if (dim == 3) return f64 ? sym_kernel_of<3, true>(sh, algo) : sym_kernel_of<3, false>(sh, algo);
+    return f64 ? sym_kernel_of<2, true>(sh, algo) : sym_kernel_of<2, false>(sh, algo);
+}
+// every shape this precision can be launched with (for the one-time shared-memory opt-in)
+const SymShape kSymShapesF32[] = {{4, 256}, {8, 128}, {4, 128}, {4, 64}};
+const SymShape kSymShapesF64[] = {{4, 256}, {2, 256}, {2, 128}, {4, 64}};
 
 int alloc_shard(nb200_ctx* ctx, Shard& s) {
     const int D = ctx->dim;
@@ -310,7 +324,7 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
         CK(cudaMemset(s.suspect, 1, tp));
         {
             // rows: per own i-tile one ordered + one triangular row, plus one row per cross-shard block
-            s.sym_rows_cap = (int)(tp / NB_SYM_ITILE + 1) * (2 + kSymMaxSlots) + 2 * (int)(tp / NB_TILE + 1);
+            s.sym_rows_cap = (int)(tp / NB_TILE + 1) * (3 + kSymMaxSlots);     // i-tiles may be as small as one source tile
             CK(cudaMalloc(&s.sym_rows, (size_t)s.sym_rows_cap * sizeof(NbSymRow)));
             CK(cudaMalloc(&s.sym_prefix, (size_t)(s.sym_rows_cap + 1) * sizeof(int)));
             CK(cudaMalloc(&s.gacc, 3 * (size_t)ctx->nalloc * sizeof(double)));
@@ -334,12 +348,10 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
             CK(cudaFuncSetAttribute((const void*)pick_kernel(D, ctx->f64, v, fl != 0),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem_bytes(D, ctx->f64)));
-    for (int ti = 4; ti <= (ctx->f64 ? 4 : 8); ti += 4)
-        for (int algo = 0; algo <= (ctx->f64 ? 0 : 2); ++algo)
-            CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, ti, 0, algo), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)nb_sym_smem_bytes(D, NB_SYM_ITILE / ti, ctx->f64)));
-    CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, 4, 64), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)nb_sym_smem_bytes(D, 64, ctx->f64)));
+    for (const SymShape& sh : ctx->f64 ? kSymShapesF64 : kSymShapesF32)
+        for (int algo = 0; algo <= (sh.block == 64 ? 0 : ctx->f64 ? 1 : 2); ++algo)
+            CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, sh, algo), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo)));
     return NB200_OK;
 }
 
@@ -681,18 +693,27 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     const bool cross = ctx->world > 1;
     const int W = ctx->world;
     const int tiles = (int)ctx->tiles_per_shard;
-    // two register-block shapes of the same 1024-target i-tile: 4 targets x 256 threads, 8 x 128
-    // (auto: the 2D chain is shorter, so the per-iteration reduction weighs more: 8 targets per thread there)
-    const int want_ti = ctx->opt_sym_ti ? ctx->opt_sym_ti : (D == 2 ? 8 : 4);
+    // shape = targets per thread x threads per CTA (i-tile = their product); options "sym_ti", "sym_block"
+    //   FP32: 8 x 128 (default: fewest hand-overs per chain), 4 x 256, 4 x 128
+    //   FP64: 4 x 256 (one CTA per SM), 2 x 256 and 2 x 128 (two / four CTAs per SM under 128 registers)
     // opt-in shape for small problems on one shard: i-tiles of ONE source tile (4 targets x 64 threads, many
     // small CTAs); option "sym_itile" = 256 selects it
     const bool small = !cross && (ctx->opt_sym_itile ? ctx->opt_sym_itile == 256 : (kSymSmallN > 0 && ctx->n < kSymSmallN));
-    const int ti = small ? 4 : (!ctx->f64 && want_ti == 8) ? 8 : 4;
-    const int block = small ? 64 : NB_SYM_ITILE / ti;
+    SymShape sh{4, 64};
+    if (!small) {
+        if (ctx->f64) {
+            sh.ti = ctx->opt_sym_ti == 2 ? 2 : ctx->opt_sym_ti == 4 ? 4 : kSymTiF64;
+            sh.block = (sh.ti == 2 && ctx->opt_sym_block == 128) ? 128 : 256;
+        } else {
+            sh.ti = ctx->opt_sym_ti == 8 ? 8 : ctx->opt_sym_ti == 4 ? 4 : kSymTiF32;
+            sh.block = sh.ti == 8 ? 128 : ctx->opt_sym_block == 128 ? 128 : 256;
+        }
+    }
+    const int ti = sh.ti, block = sh.block;
     const int itile = ti * block;
-    const int algo = (ctx->f64 || small) ? 0 : (ctx->opt_sym_algo >= 0 ? ctx->opt_sym_algo : kSymAlgoDefault);
-    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, ti, small ? 64 : 0, algo);
-    const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64);
+    const int algo = small ? 0 : std::min(ctx->opt_sym_algo >= 0 ? ctx->opt_sym_algo : kSymAlgoDefault, ctx->f64 ? 1 : 2);
+    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, sh, algo);
+    const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64, ti, algo);
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kfn, block, smem));
     const int resident = std::max(1, nb) * s.sms;
@@ -1182,7 +1203,8 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "trace")) ctx->opt_trace = value != 0;
     else if (!strcmp(key, "detect")) ctx->opt_detect = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "symmetric")) ctx->opt_symmetric = value < 0 ? -1 : (value != 0);
-    else if (!strcmp(key, "sym_ti")) ctx->opt_sym_ti = value == 8 ? 8 : value == 4 ? 4 : 0;
+    else if (!strcmp(key, "sym_ti")) ctx->opt_sym_ti = (value == 8 || value == 4 || value == 2) ? (int)value : 0;
+    else if (!strcmp(key, "sym_block")) ctx->opt_sym_block = (value == 128 || value == 256) ? (int)value : 0;
     else if (!strcmp(key, "sym_algo")) ctx->opt_sym_algo = (value >= 0 && value <= 2) ? (int)value : -1;
     else if (!strcmp(key, "sym_itile")) ctx->opt_sym_itile = value == 256 ? 256 : value == 1024 ? 1024 : 0;
     else if (!strcmp(key, "exchange")) {
@@ -1594,6 +1616,46 @@ int nb200_accuracy_pct(nb200_ctx* ctx, const double* forces, const double* refer
         ok += h;
     }
     *pct = ctx->n ? 100.0 * (double)ok / (double)ctx->n : 0.0;
+    return NB200_OK;
+}
+
+int nb200_compare_forces(nb200_ctx* ctx, nb200_ctx* other, double* stats_out) {
+    if (!ctx || !other || !stats_out) return NB200_EINVAL;
+    if (ctx->dim != other->dim || ctx->n != other->n || ctx->shards.size() != other->shards.size() ||
+        ctx->world != other->world)
+        return fail(ctx, NB200_EINVAL, "compare: the two contexts differ in dim, n or shard layout");
+    for (int k = 0; k < NB200_COMPARE_STATS; ++k) stats_out[k] = 0.0;
+    const int D = ctx->dim;
+    for (size_t i = 0; i < ctx->shards.size(); ++i) {
+        Shard& s = ctx->shards[i];
+        Shard& o = other->shards[i];
+        if (s.device != o.device || s.tgt_base != o.tgt_base || s.n_local != o.n_local)
+            return fail(ctx, NB200_EINVAL, "compare: shard %zu lives on different devices or rows", i);
+        if (s.n_local <= 0) continue;
+        if (!s.forces_valid || !o.forces_valid)
+            return fail(ctx, NB200_ESTATE, "compare needs a preceding nb200_forces call on both contexts");
+        CK(cudaSetDevice(s.device));
+        CK(cudaStreamSynchronize(o.compute));
+        unsigned long long* acc = nullptr;
+        CK(cudaMalloc(&acc, (2 + NB_CMP_BINS) * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(acc, 0, (2 + NB_CMP_BINS) * sizeof(unsigned long long), s.compute));
+        const int blocks = (int)((s.n_local + 255) / 256);
+        if (D == 3) nb_compare_kernel<3><<<blocks, 256, 0, s.compute>>>(s.forces, o.forces, s.n_local, s.tgt_base, acc);
+        else nb_compare_kernel<2><<<blocks, 256, 0, s.compute>>>(s.forces, o.forces, s.n_local, s.tgt_base, acc);
+        cudaError_t e = cudaGetLastError();
+        unsigned long long h[2 + NB_CMP_BINS];
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, acc, sizeof h, cudaMemcpyDeviceToHost, s.compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s.compute);
+        cudaFree(acc);
+        if (e != cudaSuccess) return fail(ctx, NB200_ECUDA, "compare kernel: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        double mx;
+        memcpy(&mx, &h[0], sizeof mx);
+        stats_out[0] += (double)s.n_local;
+        if (mx > stats_out[1]) { stats_out[1] = mx; stats_out[2] = (double)h[1]; }
+        stats_out[3] += (double)h[2 + NB_CMP_BINS - 1];
+        for (int k = 0; k < NB_CMP_BINS - 1; ++k) stats_out[4 + k] += (double)h[2 + k];
+    }
     return NB200_OK;
 }
 

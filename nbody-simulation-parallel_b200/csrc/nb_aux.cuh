@@ -339,6 +339,47 @@ __global__ void __launch_bounds__(256) nb_accuracy_kernel(const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-body norm-wise relative difference ||F_a - F_b|| / ||F_b|| of two force arrays resident on the
+// device, over ALL bodies: maximum (value and body), and a histogram by decade.  This is the
+// full-population form of the parity metric (tests/test_gpu_parity.py) for sizes where the CPU
+// oracle can only cover sampled targets: FP32 mode against an FP64 context holding the same bodies.
+//   out[0] = bit pattern of the max (non-negative doubles order like their bits), out[1] = body of the max,
+//   out[2 + k] = bodies with difference in [10^(k-17), 10^(k-16)), k = 1..17; k = 0: below 1e-16 (or both zero);
+//   out[2 + 18] = non-finite differences
+#define NB_CMP_BINS 19
+template <int D>
+__global__ void __launch_bounds__(256) nb_compare_kernel(const double* __restrict__ fa, const double* __restrict__ fb,
+                                                          long long n, long long index_base,
+                                                          unsigned long long* __restrict__ out) {
+    __shared__ unsigned hist[NB_CMP_BINS];
+    if (threadIdx.x < NB_CMP_BINS) hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double num = 0.0, den = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const double a = fa[i * D + d], b = fb[i * D + d];
+            num = fma(a - b, a - b, num);
+            den = fma(b, b, den);
+        }
+        const double rel = (num == 0.0) ? 0.0 : sqrt(num / den);      // den = 0 with num > 0: inf
+        int bin;
+        if (!isfinite(rel)) bin = NB_CMP_BINS - 1;
+        else if (rel < 1e-16) bin = 0;
+        else bin = min(NB_CMP_BINS - 2, max(1, (int)floor(log10(rel)) + 17));
+        atomicAdd(&hist[bin], 1u);
+        if (isfinite(rel)) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(rel);
+            const unsigned long long old = atomicMax(&out[0], bits);
+            if (bits > old) out[1] = (unsigned long long)(index_base + i);   // racy between equal maxima only: any of them
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NB_CMP_BINS && hist[threadIdx.x]) atomicAdd(&out[2 + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Measured FP32 FMA-pipe peak of the device the roofline is quoted against (MEASURED_PEAKS.json
 // holds only HBM and bf16-tensor peaks): independent packed FFMA2 chains acc = x*x + acc, eight per
 // thread, two operands each so the register file is not the limit (tools/ubench.cu: 97 % of

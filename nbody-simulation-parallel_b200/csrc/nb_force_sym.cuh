@@ -24,6 +24,8 @@
 // units of other i-tiles and, across ranks, from other GPUs: nb_sym_push_kernel), so
 // nb_finish_kernel runs after the pass.
 #pragma once
+#include <algorithm>
+
 #include "nb_force.cuh"
 
 #define NB_SYM_ITILE 1024                           // targets per i-tile (TI * BLOCK) of the large shapes = 4 source tiles;
@@ -46,7 +48,16 @@ struct NbSymRow {
 #define NB_ROT_UNROLL 1
 #endif
 #ifndef NB_ROT_SHFL_ASM
-#define NB_ROT_SHFL_ASM 0
+#define NB_ROT_SHFL_ASM 1     // in-place shfl.sync: 3675 vs 3534 G inter/s at N = 2^20 (no MOVs at the loop end)
+#endif
+#ifndef NB_ROT_ORDER
+#define NB_ROT_ORDER 0
+#endif
+#ifndef NB_ROT_PIPE
+#define NB_ROT_PIPE 0         // 1: source pairs loaded half a step ahead of their use (LDS.64, no extra registers)
+#endif
+#ifndef NB_ROT_SMEM_ACC
+#define NB_ROT_SMEM_ACC 1     // FP64 per-target sums in shared memory: 3810 vs 3675 (24 registers back for the chains)
 #endif
 
 struct NbSymParams {
@@ -92,11 +103,28 @@ struct NbSymFinish {
     unsigned* done;              // CTA completion counter for the step signal (self-resetting)
 };
 
-static inline size_t nb_sym_smem_bytes(int dim, int block, bool f64) {
+// TMA ring depth of a shape: the 4 x 128 FP32 shape runs five CTAs per SM and has room for two stages only
+// (one tile takes ~10 us to consume, a bulk copy ~1 us to land: two are enough)
+__host__ __device__ constexpr int nb_sym_stages(bool f64, int ti, int block) {
+    return ((!f64 && ti == 4 && block == 128) || (f64 && ti == 2)) ? 2 : NB_STAGES;
+}
+// resident CTAs per SM the register allocation is capped for
+__host__ __device__ constexpr int nb_sym_min_blocks(bool f64, int ti, int block) {
+    return block == 64 ? (f64 ? 4 : 7)
+           : f64 ? (ti == 2 ? (block == 256 ? 2 : 4) : 1)
+                 : block == 256 ? 2 : (ti == 8 ? 3 : 5);
+}
+
+static inline size_t nb_sym_smem_bytes(int dim, int block, bool f64, int ti = 0, int algo = 0) {
     const size_t rs = f64 ? 8 : 4;
-    const size_t ring = (size_t)NB_STAGES * NB_TILE * (dim + 1) * rs;
-    const size_t bars = 2 * NB_STAGES * sizeof(uint64_t) + 16;
-    const size_t scr = (size_t)(block / 32) * 2 * 32 * NB_SYM_ROW * sizeof(float);
+    if (ti == 0) ti = block == 64 ? 4 : NB_SYM_ITILE / block;
+    const int stages = nb_sym_stages(f64, ti, block);
+    const size_t ring = (size_t)stages * NB_TILE * (dim + 1) * rs;
+    const size_t bars = 2 * stages * sizeof(uint64_t) + 16;
+    // transpose scratch of sym_algo 0; the rotation flavours keep the FP64 per-target sums there
+    // ([TI * 3][block] doubles)
+    const size_t scr = std::max(algo == 0 ? (size_t)(block / 32) * 2 * 32 * NB_SYM_ROW * sizeof(float) : (size_t)0,
+                                (f64 || algo == 0) ? (size_t)0 : (size_t)3 * ti * block * sizeof(double));
     const size_t bout = (size_t)2 * (block / 32) * dim * NB_TILE * rs;
     return ring + bars + scr + bout;
 }
@@ -226,10 +254,11 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
                                                     const float (&npos)[TI][3],
                                                     const float (&mi)[TI],
                                                     float2 (&a)[TI][3], float* __restrict__ wout, int lane) {
-    const float4* sx = reinterpret_cast<const float4*>(stage);
-    const float4* sy = sx + NB_TILE / 4;
-    const float4* sz = sy + NB_TILE / 4;                      // D == 3 only
-    const float4* sm = sx + D * (NB_TILE / 4);
+    // plane p of the stage as float2: source pair (group g, half h) sits at p * (NB_TILE / 2) + 2 g + h
+    const float2* sx = reinterpret_cast<const float2*>(stage);
+    const float2* sy = sx + NB_TILE / 2;
+    const float2* sz = sy + NB_TILE / 2;                      // D == 3 only
+    const float2* sm = sx + D * (NB_TILE / 2);
 #pragma unroll
     for (int t = 0; t < TI; ++t)
 #pragma unroll
@@ -237,19 +266,112 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
     const float inf = __int_as_float(0x7f800000);
     const int from = (lane + 1) & 31;
 
+    // the TI chains of one pair of sources: target sums a, reaction sums b
+    auto chains = [&](const float2 xs, const float2 ys, const float2 zs, const float2 ms, float2 (&b)[3]) {
+#pragma unroll
+        for (int t = 0; t < TI; ++t) {
+            const float2 dx = __fadd2_rn(xs, make_float2(npos[t][0], npos[t][0]));
+            const float2 dy = __fadd2_rn(ys, make_float2(npos[t][1], npos[t][1]));
+            float2 r2 = __fmul2_rn(dx, dx);
+            r2 = __ffma2_rn(dy, dy, r2);
+            float2 dz;
+            if (D == 3) {
+                dz = __fadd2_rn(zs, make_float2(npos[t][2], npos[t][2]));
+                r2 = __ffma2_rn(dz, dz, r2);
+            }
+            if (MODE == NB_EXACT) {
+                r2.x = (r2.x >= cutoff) ? r2.x : inf;
+                r2.y = (r2.y >= cutoff) ? r2.y : inf;
+            }
+            float2 inv;
+            inv.x = nb_rcp_f32(r2.x);
+            inv.y = nb_rcp_f32(r2.y);
+            const float2 w = __fmul2_rn(inv, inv);
+            const float2 s = __fmul2_rn(w, ms);
+            const float2 u = __fmul2_rn(w, make_float2(mi[t], mi[t]));
+#if NB_ROT_ORDER == 1
+            // s shared by the first three, u by the last three, dz by the middle two (operand reuse cache)
+            a[t][0] = __ffma2_rn(dx, s, a[t][0]);
+            a[t][1] = __ffma2_rn(dy, s, a[t][1]);
+            if (D == 3) {
+                a[t][2] = __ffma2_rn(dz, s, a[t][2]);
+                b[2] = __ffma2_rn(dz, u, b[2]);
+            }
+            b[1] = __ffma2_rn(dy, u, b[1]);
+            b[0] = __ffma2_rn(dx, u, b[0]);
+#else
+            a[t][0] = __ffma2_rn(dx, s, a[t][0]);
+            b[0] = __ffma2_rn(dx, u, b[0]);
+            a[t][1] = __ffma2_rn(dy, s, a[t][1]);
+            b[1] = __ffma2_rn(dy, u, b[1]);
+            if (D == 3) {
+                a[t][2] = __ffma2_rn(dz, s, a[t][2]);
+                b[2] = __ffma2_rn(dz, u, b[2]);
+            }
+#endif
+        }
+    };
+    // this pair of sources is done for this lane: pass its sums on to lane l - 1
+    auto hand_over = [&](float2 (&trav)[3], const float2 (&b)[3]) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            float2 v = DECOUPLE ? __fadd2_rn(trav[d], b[d]) : b[d];
+#if NB_ROT_SHFL_ASM
+            // in-place shuffles: the loop-carried pair keeps its registers (no MOVs at the loop end)
+            asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+f"(v.x) : "r"(from));
+            asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+f"(v.y) : "r"(from));
+            trav[d] = v;
+#else
+            trav[d].x = __shfl_sync(0xffffffffu, v.x, from);
+            trav[d].y = __shfl_sync(0xffffffffu, v.y, from);
+#endif
+        }
+    };
+    const float2 zero2 = make_float2(0.f, 0.f);
+
 #pragma unroll 1
     for (int hf = 0; hf < NB_TILE / 128; ++hf) {
-        float2 trav[2][3];                                    // sums of the group this lane meets NEXT (or met, see below)
+        float2 trav[2][3];                                    // travelling sums of the group this lane meets next
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int d = 0; d < 3; ++d) trav[h][d] = make_float2(0.f, 0.f);
+            for (int d = 0; d < 3; ++d) trav[h][d] = zero2;
+#if NB_ROT_PIPE
+        // loads half a step ahead of their use: the first pair of the NEXT group is fetched while the second
+        // pair of this group is worked on, the second pair of this group while the first pair is
+        int g = hf * 64 + 2 * lane;
+        float2 Ax = sx[g], Ay = sy[g], Am = sm[g], Az = zero2;
+        if (D == 3) Az = sz[g];
+#endif
         NB_UNROLL(NB_ROT_UNROLL)
         for (int k = 0; k < 32; ++k) {
+#if NB_ROT_PIPE
+            const float2 Bx = sx[g + 1], By = sy[g + 1], Bm = sm[g + 1];
+            float2 Bz = zero2;
+            if (D == 3) Bz = sz[g + 1];
+            g = hf * 64 + 2 * ((lane + k + 1) & 31);
+            {
+                float2 b[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) b[d] = DECOUPLE ? zero2 : trav[0][d];
+                chains(Ax, Ay, Az, Am, b);
+                hand_over(trav[0], b);
+            }
+            Ax = sx[g]; Ay = sy[g]; Am = sm[g];
+            if (D == 3) Az = sz[g];
+            {
+                float2 b[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) b[d] = DECOUPLE ? zero2 : trav[1][d];
+                chains(Bx, By, Bz, Bm, b);
+                hand_over(trav[1], b);
+            }
+#else
             const int q = hf * 32 + ((lane + k) & 31);
-            const float4 X = sx[q], Y = sy[q], M = sm[q];
+            const float4 X = reinterpret_cast<const float4*>(sx)[q], Y = reinterpret_cast<const float4*>(sy)[q],
+                         M = reinterpret_cast<const float4*>(sm)[q];
             float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (D == 3) Z = sz[q];
+            if (D == 3) Z = reinterpret_cast<const float4*>(sz)[q];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const float2 xs = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
@@ -258,52 +380,11 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
                 const float2 ms = h ? make_float2(M.z, M.w) : make_float2(M.x, M.y);
                 float2 b[3];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) b[d] = DECOUPLE ? make_float2(0.f, 0.f) : trav[h][d];
-#pragma unroll
-                for (int t = 0; t < TI; ++t) {
-                    const float2 dx = __fadd2_rn(xs, make_float2(npos[t][0], npos[t][0]));
-                    const float2 dy = __fadd2_rn(ys, make_float2(npos[t][1], npos[t][1]));
-                    float2 r2 = __fmul2_rn(dx, dx);
-                    r2 = __ffma2_rn(dy, dy, r2);
-                    float2 dz;
-                    if (D == 3) {
-                        dz = __fadd2_rn(zs, make_float2(npos[t][2], npos[t][2]));
-                        r2 = __ffma2_rn(dz, dz, r2);
-                    }
-                    if (MODE == NB_EXACT) {
-                        r2.x = (r2.x >= cutoff) ? r2.x : inf;
-                        r2.y = (r2.y >= cutoff) ? r2.y : inf;
-                    }
-                    float2 inv;
-                    inv.x = nb_rcp_f32(r2.x);
-                    inv.y = nb_rcp_f32(r2.y);
-                    const float2 w = __fmul2_rn(inv, inv);
-                    const float2 s = __fmul2_rn(w, ms);
-                    const float2 u = __fmul2_rn(w, make_float2(mi[t], mi[t]));
-                    a[t][0] = __ffma2_rn(dx, s, a[t][0]);
-                    b[0] = __ffma2_rn(dx, u, b[0]);
-                    a[t][1] = __ffma2_rn(dy, s, a[t][1]);
-                    b[1] = __ffma2_rn(dy, u, b[1]);
-                    if (D == 3) {
-                        a[t][2] = __ffma2_rn(dz, s, a[t][2]);
-                        b[2] = __ffma2_rn(dz, u, b[2]);
-                    }
-                }
-                // this pair of sources is done for this lane: pass its sums on to lane l - 1
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    float2 v = DECOUPLE ? __fadd2_rn(trav[h][d], b[d]) : b[d];
-#if NB_ROT_SHFL_ASM
-                    // in-place shuffles: the loop-carried pair keeps its registers (no MOVs at the loop end)
-                    asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+f"(v.x) : "r"(from));
-                    asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+f"(v.y) : "r"(from));
-                    trav[h][d] = v;
-#else
-                    trav[h][d].x = __shfl_sync(0xffffffffu, v.x, from);
-                    trav[h][d].y = __shfl_sync(0xffffffffu, v.y, from);
-#endif
-                }
+                for (int d = 0; d < 3; ++d) b[d] = DECOUPLE ? zero2 : trav[h][d];
+                chains(xs, ys, zs, ms, b);
+                hand_over(trav[h], b);
             }
+#endif
         }
         // after 32 hand-overs the sums of home group `lane` are complete and back in lane `lane`
         float4* wo = reinterpret_cast<float4*>(wout + hf * 128 + 4 * lane);
@@ -398,10 +479,82 @@ __device__ __forceinline__ void nb_tile_f64_sym(const double* __restrict__ stage
     __syncwarp();
 }
 
-// ALGO (FP32 only): 0 = shared-memory transpose, 1 = register rotation, 2 = register rotation, decoupled
+// FP64, reaction sums rotated through the warp (see nb_tile_f32_sym_rot): a quarter tile = 64 sources =
+// 32 home groups of two, one LDS.128 per plane and step, 12 SHFL (six doubles) per 2 x TI chains.
+template <int D, int TI, bool EXACT>
+__device__ __forceinline__ void nb_tile_f64_sym_rot(const double* __restrict__ stage, double cutoff,
+                                                    const double (&pos)[TI][3], const double (&mi)[TI],
+                                                    double (&accd)[TI][3], double* __restrict__ wout, int lane) {
+    const double2* sx = reinterpret_cast<const double2*>(stage);
+    const double2* sy = sx + NB_TILE / 2;
+    const double2* sz = sy + NB_TILE / 2;                     // D == 3 only
+    const double2* sm = sx + D * (NB_TILE / 2);
+    const int from = (lane + 1) & 31;
+#pragma unroll 1
+    for (int qd = 0; qd < NB_TILE / 64; ++qd) {
+        double trav[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) trav[h][d] = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < 32; ++k) {
+            const int g = qd * 32 + ((lane + k) & 31);
+            const double2 X = sx[g], Y = sy[g], M = sm[g];
+            double2 Z = make_double2(0.0, 0.0);
+            if (D == 3) Z = sz[g];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double xs = h ? X.y : X.x, ys = h ? Y.y : Y.x, zs = h ? Z.y : Z.x;
+                const double ms = h ? M.y : M.x;
+                double b[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) b[d] = trav[h][d];
+#pragma unroll
+                for (int t = 0; t < TI; ++t) {
+                    const double dx = xs - pos[t][0];
+                    const double dy = ys - pos[t][1];
+                    double r2 = dx * dx;
+                    r2 = fma(dy, dy, r2);
+                    double dz = 0.0;
+                    if (D == 3) {
+                        dz = zs - pos[t][2];
+                        r2 = fma(dz, dz, r2);
+                    }
+                    double inv = nb_rcp_f64(r2);
+                    if (EXACT) inv = (r2 >= cutoff) ? inv : 0.0;  // drop (also kills the NaN of r2 = 0)
+                    const double w = inv * inv;
+                    const double s = w * ms;
+                    const double u = w * mi[t];
+                    accd[t][0] = fma(dx, s, accd[t][0]);
+                    b[0] = fma(dx, u, b[0]);
+                    accd[t][1] = fma(dy, s, accd[t][1]);
+                    b[1] = fma(dy, u, b[1]);
+                    if (D == 3) {
+                        accd[t][2] = fma(dz, s, accd[t][2]);
+                        b[2] = fma(dz, u, b[2]);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    int lo = __double2loint(b[d]), hi = __double2hiint(b[d]);
+                    asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(lo) : "r"(from));
+                    asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(hi) : "r"(from));
+                    trav[h][d] = __hiloint2double(hi, lo);
+                }
+            }
+        }
+        double2* wo = reinterpret_cast<double2*>(wout + qd * 64 + 2 * lane);
+#pragma unroll
+        for (int d = 0; d < D; ++d) wo[d * (NB_TILE / 2)] = make_double2(trav[0][d], trav[1][d]);
+    }
+}
+
+// ALGO: 0 = shared-memory transpose of the reaction sums, 1 = register rotation, 2 (FP32) = rotation, decoupled
 template <int D, bool F64, int TI, int BLOCK, int ALGO = 0>
-__global__ void __launch_bounds__(BLOCK, BLOCK == 64 ? (F64 ? 4 : 7) : F64 ? 1 : (BLOCK == 256 ? 2 : 3))
+__global__ void __launch_bounds__(BLOCK, nb_sym_min_blocks(F64, TI, BLOCK))
 nb_force_sym_kernel(const NbSymParams P) {
+    constexpr int STAGES = nb_sym_stages(F64, TI, BLOCK);
     using real = typename NbReal<F64>::type;
     constexpr int NP = D + 1;
     constexpr int ITILE = TI * BLOCK;
@@ -412,11 +565,13 @@ nb_force_sym_kernel(const NbSymParams P) {
 
     extern __shared__ __align__(128) unsigned char nb_smem[];
     real* ring = reinterpret_cast<real*>(nb_smem);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(nb_smem + (size_t)NB_STAGES * TILE_BYTES);
-    uint64_t* empty_bar = full_bar + NB_STAGES;
-    int* s_unit = reinterpret_cast<int*>(empty_bar + NB_STAGES);   // [0] i-tile (or -1), [1] segment
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(nb_smem + (size_t)STAGES * TILE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    int* s_unit = reinterpret_cast<int*>(empty_bar + STAGES);   // [0] i-tile (or -1), [1] segment
     float* scr_all = reinterpret_cast<float*>(s_unit + 4);
-    real* bout_all = reinterpret_cast<real*>(scr_all + (size_t)NWARPS * 2 * 32 * NB_SYM_ROW);   // [2][NWARPS][D][NB_TILE]
+    // ALGO 0: the transpose scratch; FP32 rotation: the FP64 per-target sums; FP64 rotation: nothing
+    constexpr size_t SCR_FLOATS = ALGO == 0 ? (size_t)NWARPS * 2 * 32 * NB_SYM_ROW : F64 ? (size_t)0 : (size_t)6 * ITILE;
+    real* bout_all = reinterpret_cast<real*>(scr_all + SCR_FLOATS);   // [2][NWARPS][D][NB_TILE]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -424,7 +579,7 @@ nb_force_sym_kernel(const NbSymParams P) {
     float* scr = scr_all + (size_t)warp * 2 * 32 * NB_SYM_ROW;
 
     if (tid == 0) {
-        for (int s = 0; s < NB_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             nb_mbar_init(&full_bar[s], 1);
             nb_mbar_init(&empty_bar[s], NWARPS);
         }
@@ -464,11 +619,11 @@ nb_force_sym_kernel(const NbSymParams P) {
         const int ntl = te - ts;
 
         if (tid == 0) {
-            const int pre = min(NB_STAGES - 1, ntl);
+            const int pre = min(STAGES - 1, ntl);
             for (int t = 0; t < pre; ++t) {
                 const unsigned k = kt + t;
-                const int slot = k % NB_STAGES;
-                nb_mbar_wait(&empty_bar[slot], ((k / NB_STAGES) & 1u) ^ 1u);
+                const int slot = k % STAGES;
+                nb_mbar_wait(&empty_bar[slot], ((k / STAGES) & 1u) ^ 1u);
                 nb_mbar_expect_tx(&full_bar[slot], TILE_BYTES);
                 nb_tma_load_1d(ring + (size_t)slot * TILE_ELEMS, src + (size_t)(ts + t) * TILE_ELEMS,
                                TILE_BYTES, &full_bar[slot]);
@@ -497,9 +652,6 @@ nb_force_sym_kernel(const NbSymParams P) {
             suspect |= P.suspect[it * ITILE + tid + t * BLOCK] != 0;
         }
         const bool warp_suspect = __any_sync(0xffffffffu, suspect) != 0;
-#ifndef NB_ROT_SMEM_ACC
-#define NB_ROT_SMEM_ACC 0
-#endif
         // FP64 sums of the own targets over the unit: in registers, or (rotation flavours, experiment) in the
         // shared memory the transpose scratch no longer needs -- 24 registers back for the chains
         constexpr bool SACC = NB_ROT_SMEM_ACC && !F64 && ALGO != 0;
@@ -516,18 +668,18 @@ nb_force_sym_kernel(const NbSymParams P) {
         }
 
         for (int t = 0; t < ntl; ++t) {
-            if (tid == 0 && t + NB_STAGES - 1 < ntl) {
-                const unsigned k = kt + t + NB_STAGES - 1;
-                const int slot = k % NB_STAGES;
-                nb_mbar_wait(&empty_bar[slot], ((k / NB_STAGES) & 1u) ^ 1u);
+            if (tid == 0 && t + STAGES - 1 < ntl) {
+                const unsigned k = kt + t + STAGES - 1;
+                const int slot = k % STAGES;
+                nb_mbar_wait(&empty_bar[slot], ((k / STAGES) & 1u) ^ 1u);
                 nb_mbar_expect_tx(&full_bar[slot], TILE_BYTES);
                 nb_tma_load_1d(ring + (size_t)slot * TILE_ELEMS,
-                               src + (size_t)(ts + t + NB_STAGES - 1) * TILE_ELEMS, TILE_BYTES,
+                               src + (size_t)(ts + t + STAGES - 1) * TILE_ELEMS, TILE_BYTES,
                                &full_bar[slot]);
             }
             const unsigned k = kt + t;
-            const int slot = k % NB_STAGES;
-            nb_mbar_wait(&full_bar[slot], (k / NB_STAGES) & 1u);
+            const int slot = k % STAGES;
+            nb_mbar_wait(&full_bar[slot], (k / STAGES) & 1u);
             const real* stage = ring + (size_t)slot * TILE_ELEMS;
             real* wout = bout_all + ((size_t)bbuf * NWARPS + warp) * (D * NB_TILE);
             bool exact_tile = warp_suspect;
@@ -543,8 +695,13 @@ nb_force_sym_kernel(const NbSymParams P) {
                 double* dscr = reinterpret_cast<double*>(scr);
                 double* dwout = reinterpret_cast<double*>(wout);
                 if (sym) {
-                    if (exact_tile) nb_tile_f64_sym<D, TI, true>(dstage, P.cutoff, pos, mid, accd, dscr, dwout, lane);
-                    else nb_tile_f64_sym<D, TI, false>(dstage, P.cutoff, pos, mid, accd, dscr, dwout, lane);
+                    if constexpr (ALGO == 0) {
+                        if (exact_tile) nb_tile_f64_sym<D, TI, true>(dstage, P.cutoff, pos, mid, accd, dscr, dwout, lane);
+                        else nb_tile_f64_sym<D, TI, false>(dstage, P.cutoff, pos, mid, accd, dscr, dwout, lane);
+                    } else {
+                        if (exact_tile) nb_tile_f64_sym_rot<D, TI, true>(dstage, P.cutoff, pos, mid, accd, dwout, lane);
+                        else nb_tile_f64_sym_rot<D, TI, false>(dstage, P.cutoff, pos, mid, accd, dwout, lane);
+                    }
                 } else {
                     if (exact_tile) nb_tile_f64<D, TI, 1, true>(dstage, 0, P.cutoff, pos, accd);
                     else nb_tile_f64<D, TI, 1, false>(dstage, 0, P.cutoff, pos, accd);

@@ -74,6 +74,7 @@ class _Oracle:
                                       ctypes.c_double, ctypes.c_int, ctypes.c_int]
         L.oracle_energy.argtypes = [ctypes.c_int, sz, _dp, ctypes.c_double, ctypes.c_double, _dp, _dp]
         L.oracle_condition.argtypes = [ctypes.c_int, sz, _dp, ctypes.c_double, ctypes.c_double, _dp]
+        L.oracle_condition_targets.argtypes = [ctypes.c_int, sz, _dp, ctypes.c_double, ctypes.c_double, _ip, sz, _dp]
         L.oracle_accuracy_pct.argtypes = [ctypes.c_int, sz, _dp, _dp]
         L.oracle_accuracy_pct.restype = ctypes.c_double
         L.oracle_num_threads.restype = ctypes.c_int
@@ -150,6 +151,18 @@ def condition(bodies, G=G_REF, cutoff=CUTOFF_REF):
     rc = _o().oracle_condition(dim, b.shape[0], _p(b), G, cutoff, _p(out))
     if rc:
         raise RuntimeError(f"oracle condition rc={rc}")
+    return out
+
+
+def condition_targets(bodies, targets, G=G_REF, cutoff=CUTOFF_REF):
+    """kappa of a subset of targets (all sources)."""
+    dim = _dim_of(bodies)
+    b = _as_bodies(bodies, dim)
+    t = np.ascontiguousarray(targets, dtype=np.int64)
+    out = np.ones(t.shape[0])
+    rc = _o().oracle_condition_targets(dim, b.shape[0], _p(b), G, cutoff, t.ctypes.data_as(_ip), t.shape[0], _p(out))
+    if rc:
+        raise RuntimeError(f"oracle condition_targets rc={rc}")
     return out
 
 

@@ -289,6 +289,35 @@ int oracle_condition(int D, size_t n, const double *bodies, double G, double cut
     return 0;
 }
 
+/* kappa of a subset of targets (all sources): lets the FP32 criterion be applied to sampled targets
+ * at sizes where the full O(N^2) pass above is out of reach. */
+int oracle_condition_targets(int D, size_t n, const double *bodies, double G, double cutoff,
+                             const long long *targets, size_t ntargets, double *kappa)
+{
+    if (D != 2 && D != 3) return -1;
+    for (size_t k = 0; k < ntargets; k++)
+        if (targets[k] < 0 || (size_t)targets[k] >= n) return -2;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (size_t k = 0; k < ntargets; k++) {
+        const size_t i = (size_t)targets[k];
+        double acc[3] = {0.0, 0.0, 0.0}, sum_abs = 0.0;
+        for (size_t j = 0; j < n; j++) {
+            double f[3], nf = 0.0;
+            if (i == j) continue;
+            if (!pair_force(D, POS(bodies, i, D), POS(bodies, j, D), MASS(bodies, i, D),
+                            MASS(bodies, j, D), G, cutoff, f))
+                continue;
+            for (int d = 0; d < D; d++) { acc[d] -= f[d]; nf += f[d] * f[d]; }
+            sum_abs += sqrt(nf);
+        }
+        double na = 0.0;
+        for (int d = 0; d < D; d++) na += acc[d] * acc[d];
+        na = sqrt(na);
+        kappa[k] = na > 0.0 ? sum_abs / na : (sum_abs > 0.0 ? INFINITY : 1.0);
+    }
+    return 0;
+}
+
 /* compute_accuracy_omp, utils.h:170-219: % of bodies whose every component is within
  * 1 % of the reference force (|ref| < 1e-20 -> absolute test |f| <= 1e-9). */
 double oracle_accuracy_pct(int D, size_t n, const double *forces, const double *ref)

@@ -485,8 +485,9 @@ def test_pair_symmetric_pass_matches_ordered_pass(pkg, oracle, dim, n, prec, seg
 
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("n", [300, 5000, 9473])
-@pytest.mark.parametrize("algo,sym_ti,seg_tiles", [(1, 4, 0), (1, 8, 3), (2, 4, 1), (2, 8, 0), (0, 4, 0)])
-def test_pair_symmetric_reduction_flavours(pkg, oracle, dim, n, algo, sym_ti, seg_tiles):
+@pytest.mark.parametrize("algo,sym_ti,seg_tiles,block", [(1, 4, 0, 0), (1, 8, 3, 0), (2, 4, 1, 0), (2, 8, 0, 0), (0, 4, 0, 0),
+                                                         (1, 4, 0, 128), (1, 4, 3, 128), (0, 4, 1, 128), (2, 4, 0, 128)])
+def test_pair_symmetric_reduction_flavours(pkg, oracle, dim, n, algo, sym_ti, seg_tiles, block):
     """The three ways the FP32 pair-symmetric kernel sums the reactions on the streamed sources
     (sym_algo 0: shared-memory transpose, 1: register rotation through the warp, 2: rotation with
     decoupled hand-over) must all reproduce the oracle: forces and a few fused steps; ragged sizes,
@@ -495,13 +496,36 @@ def test_pair_symmetric_reduction_flavours(pkg, oracle, dim, n, algo, sym_ti, se
     b[17, :dim] = b[3, :dim]
     b[101, :dim] = b[100, :dim] + 2e-6
     b = pkg.generators.round_to_float(b)
-    opts = {"detect": 1, "symmetric": 1, "sym_algo": algo, "sym_ti": sym_ti, "seg_tiles": seg_tiles}
+    opts = {"detect": 1, "symmetric": 1, "sym_algo": algo, "sym_ti": sym_ti, "seg_tiles": seg_tiles, "sym_block": block}
     f = pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32, options=opts)
     assert_fp32_parity(pkg, oracle, f, b, f"sym_algo={algo} TI={sym_ti} n={n}")
     got = pkg.brute_force_cuda_simulate(b, 1e-5, 3, pkg.NB200_FP32, options=opts)
     want = pkg.brute_force_cuda_simulate(b, 1e-5, 3, pkg.NB200_FP32, options={"detect": 1, "symmetric": 0})
     scale = np.abs(want[:, :2 * dim]).max()
     assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("n", [300, 5000, 9473])
+@pytest.mark.parametrize("algo,sym_ti,block,seg_tiles", [(1, 4, 256, 0), (1, 2, 256, 0), (1, 2, 128, 3), (0, 2, 256, 1), (0, 2, 128, 0)])
+def test_pair_symmetric_fp64_shapes(pkg, oracle, dim, n, algo, sym_ti, block, seg_tiles):
+    """FP64 pair-symmetric kernel: both reaction-sum reductions and all register-block shapes hold the
+    1e-12 bound against the oracle (forces, then a few fused steps against the ordered pass)."""
+    b = pkg.generators.uniform_cube(n, dim, seed=177 + n)
+    b[17, :dim] = b[3, :dim]
+    b[101, :dim] = b[100, :dim] + 2e-6
+    opts = {"detect": 1, "symmetric": 1, "sym_algo": algo, "sym_ti": sym_ti, "sym_block": block, "seg_tiles": seg_tiles}
+    with pkg.NBodyCuda(dim, n, pkg.NB200_FP64) as ctx:
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        ctx.upload(b)
+        f = ctx.forces()
+        assert f"pair-symmetric(TI={sym_ti},block={block}" in ctx.plan, ctx.plan
+    assert rel(pkg, f, oracle.forces(b)).max() <= TOL64
+    got = pkg.brute_force_cuda_simulate(b, 1e-5, 3, pkg.NB200_FP64, options=opts)
+    want = pkg.brute_force_cuda_simulate(b, 1e-5, 3, pkg.NB200_FP64, options={"detect": 1, "symmetric": 0})
+    scale = np.abs(want[:, :2 * dim]).max()
+    assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= 1e-12 * scale
 
 
 # ------------------------------------------------------------------ -a 1 column and validation print on the device
