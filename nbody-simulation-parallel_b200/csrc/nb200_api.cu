@@ -177,6 +177,8 @@ struct Shard {
     void* peer_src[2][NB_MAX_PEERS] = {{nullptr}};    // peers' source buffers, mapped into this device
     unsigned long long* peer_flags[NB_MAX_PEERS] = {nullptr};
     bool ipc_opened = false;                          // peer pointers came from cudaIpcOpenMemHandle
+    unsigned long long* err_host = nullptr;           // page-locked, device-mapped: what a timed-out flag wait was waiting for
+    unsigned long long* err_dev = nullptr;            // its device address
 };
 
 constexpr int kMaxWorldP2P = NB_MAX_PEERS + 1;
@@ -216,8 +218,10 @@ struct nb200_ctx {
     unsigned long long epoch = 0;        // uploads so far (published on the epoch flags)
     std::vector<unsigned long long> acc_seq_issued;   // per driven shard: pair-symmetric passes with a reaction exchange so far
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
+    bool dead = false;            // a peer handshake timed out: the ranks' step counters may have diverged
     // options
     int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0;
+    long opt_spin_timeout_ms = 30000;   // bound of every device-side wait on a peer's flag
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
     long long launches = 0;
@@ -342,6 +346,9 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
     }
     CK(cudaMalloc(&s.sched, 2 * sizeof(unsigned)));
     CK(cudaMemset(s.sched, 0, 2 * sizeof(unsigned)));
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&s.err_host), sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+    *s.err_host = 0ull;
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&s.err_dev), s.err_host, 0));
     // opt in to the dynamic shared memory of every variant once
     for (int v = 0; v < kNumVariants; ++v)
         for (int fl = 0; fl < 2; ++fl)
@@ -368,6 +375,7 @@ void free_shard(Shard& s) {
         }
     }
     cudaFree(s.flags);
+    if (s.err_host) cudaFreeHost(s.err_host);
     cudaFree(s.grid_keys); cudaFree(s.grid_counts); cudaFree(s.suspect); cudaFree(s.sym_rows); cudaFree(s.sym_prefix); cudaFree(s.gacc); cudaFree(s.sym_done);
     for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
     cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
@@ -529,11 +537,12 @@ struct PeerRanks {
 
 // one warp: lane p spins until peer p has published step >= want_step and epoch >= want_epoch
 __global__ void nb_wait_flags_kernel(const unsigned long long* flags, int stride, int n_peers, PeerRanks pr,
-                                     unsigned long long want_step, unsigned long long want_epoch) {
+                                     unsigned long long want_step, unsigned long long want_epoch,
+                                     unsigned long long timeout_ns, unsigned long long* err_word) {
     const int p = threadIdx.x;
     if (p < n_peers) {
-        while (nb_ld_acquire_sys(flags + pr.r[p]) < want_step) __nanosleep(500);
-        while (nb_ld_acquire_sys(flags + stride + pr.r[p]) < want_epoch) __nanosleep(500);
+        nb_wait_flag(flags + pr.r[p], want_step, timeout_ns, err_word, NB_WAIT_STEP, pr.r[p]) &&
+            nb_wait_flag(flags + stride + pr.r[p], want_epoch, timeout_ns, err_word, NB_WAIT_EPOCH, pr.r[p]);
     }
 }
 
@@ -576,6 +585,8 @@ NbForceParams base_params(const nb200_ctx* ctx, const Shard& s, int mode, double
     P.wait_epoch = hs.wait_epoch;
     P.signal_step = hs.signal_step;
     P.flag_stride = kMaxWorldP2P;
+    P.err_word = s.err_dev;
+    P.spin_timeout_ns = (unsigned long long)std::max(1L, ctx->opt_spin_timeout_ms) * 1000000ull;
     if (hs.exchange) {
         P.n_peers = s.n_peers;
         for (int p = 0; p < s.n_peers; ++p) {
@@ -776,6 +787,7 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
             F.slot[F.n_src] = reinterpret_cast<const double*>(reinterpret_cast<const char*>(s.flags) + kFlagsBytes) +
                               (size_t)ex.slot * slot_doubles;
             F.flag[F.n_src] = s.flags + 2 * kMaxWorldP2P + q;
+            F.sender[F.n_src] = q;
             F.n_src++;
         }
         F.seq = seq;
@@ -849,6 +861,20 @@ int finish_timing(nb200_ctx* ctx) {
         worst = std::max(worst, (double)ms);
     }
     ctx->last_ms = worst;
+    // a flag wait that ran out of time left a record: the result of this call is void and, since the ranks'
+    // step counters may no longer agree, so is the context
+    for (Shard& s : ctx->shards) {
+        const unsigned long long w = s.err_host ? *reinterpret_cast<volatile unsigned long long*>(s.err_host) : 0ull;
+        if (!w) continue;
+        const int kind = (int)(w >> 56), peer = (int)((w >> 48) & 0xff);
+        const unsigned long long want = w & 0xffffffffffffull;
+        ctx->dead = true;
+        return fail(ctx, NB200_ESTATE,
+                    "rank %d: peer %d did not publish %s %llu within %ld ms (crashed, not called with the same options/steps, "
+                    "or never attached); the context is unusable, destroy it on every rank",
+                    s.rank, peer, kind == (int)NB_WAIT_STEP ? "step" : kind == (int)NB_WAIT_EPOCH ? "upload epoch" : "reaction-sum pass",
+                    want, ctx->opt_spin_timeout_ms);
+    }
     return NB200_OK;
 }
 
@@ -1066,28 +1092,53 @@ int nb200_ipc_attach(nb200_ctx* ctx, const void* blobs, int count) {
     if (ctx->world > kMaxWorldP2P) return fail(ctx, NB200_EINVAL, "peer-store exchange supports up to %d GPUs", kMaxWorldP2P);
     if (ctx->uploaded && !ctx->pristine) return fail(ctx, NB200_ESTATE, "attach before the first step");
     Shard& s = ctx->shards[0];
+    if (s.ipc_opened || ctx->p2p_ready) return fail(ctx, NB200_ESTATE, "the peer-store exchange is already attached");
     CK(cudaSetDevice(s.device));
     const unsigned char* in = static_cast<const unsigned char*>(blobs);
     s.n_peers = 0;
+    // on any failure the mappings opened so far are closed again: the context stays on its NCCL communicator
+    auto undo = [&](void* a0, void* a1) {
+        if (a0) cudaIpcCloseMemHandle(a0);
+        if (a1) cudaIpcCloseMemHandle(a1);
+        for (int p = 0; p < s.n_peers; ++p) {
+            cudaIpcCloseMemHandle(s.peer_src[0][p]);
+            cudaIpcCloseMemHandle(s.peer_src[1][p]);
+            cudaIpcCloseMemHandle(s.peer_flags[p]);
+        }
+        s.n_peers = 0;
+        cudaGetLastError();
+    };
     for (int r = 0; r < count; ++r) {
         const unsigned char* b = in + (size_t)r * NB200_IPC_BYTES;
         int brank = -1, bworld = -1;
         memcpy(&brank, b + 3 * sizeof(cudaIpcMemHandle_t), 4);
         memcpy(&bworld, b + 3 * sizeof(cudaIpcMemHandle_t) + 4, 4);
-        if (brank != r || bworld != ctx->world) return fail(ctx, NB200_EINVAL, "blob %d is from rank %d of %d", r, brank, bworld);
+        if (brank != r || bworld != ctx->world) {
+            undo(nullptr, nullptr);
+            return fail(ctx, NB200_EINVAL, "blob %d is from rank %d of %d", r, brank, bworld);
+        }
         if (r == s.rank) continue;
         cudaIpcMemHandle_t h;
-        const int p = s.n_peers;
+        void *m0 = nullptr, *m1 = nullptr, *mf = nullptr;
         memcpy(&h, b, sizeof h);
-        CK(cudaIpcOpenMemHandle(&s.peer_src[0][p], h, cudaIpcMemLazyEnablePeerAccess));
-        memcpy(&h, b + sizeof h, sizeof h);
-        CK(cudaIpcOpenMemHandle(&s.peer_src[1][p], h, cudaIpcMemLazyEnablePeerAccess));
-        memcpy(&h, b + 2 * sizeof h, sizeof h);
-        void* f = nullptr;
-        CK(cudaIpcOpenMemHandle(&f, h, cudaIpcMemLazyEnablePeerAccess));
-        s.peer_flags[p] = static_cast<unsigned long long*>(f);
+        cudaError_t e = cudaIpcOpenMemHandle(&m0, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) {
+            memcpy(&h, b + sizeof h, sizeof h);
+            e = cudaIpcOpenMemHandle(&m1, h, cudaIpcMemLazyEnablePeerAccess);
+        }
+        if (e == cudaSuccess) {
+            memcpy(&h, b + 2 * sizeof h, sizeof h);
+            e = cudaIpcOpenMemHandle(&mf, h, cudaIpcMemLazyEnablePeerAccess);
+        }
+        if (e != cudaSuccess) {
+            undo(m0, m1);
+            return fail(ctx, NB200_ECUDA, "cudaIpcOpenMemHandle of rank %d's buffers failed: %s", r, cudaGetErrorString(e));
+        }
+        const int p = s.n_peers++;
+        s.peer_src[0][p] = m0;
+        s.peer_src[1][p] = m1;
+        s.peer_flags[p] = static_cast<unsigned long long*>(mf);
         s.peer_rank[p] = r;
-        s.n_peers++;
     }
     s.ipc_opened = true;
     ctx->p2p_ready = true;
@@ -1204,6 +1255,22 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "detect")) ctx->opt_detect = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "symmetric")) ctx->opt_symmetric = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "sym_ti")) ctx->opt_sym_ti = (value == 8 || value == 4 || value == 2) ? (int)value : 0;
+    else if (!strcmp(key, "spin_timeout_ms")) ctx->opt_spin_timeout_ms = value > 0 ? value : 30000;
+    else if (!strcmp(key, "debug_fake_peer")) {
+        // test hook for the failure path (one GPU, no second process): a detached shard treats its OWN buffers as the
+        // buffers of its neighbour rank, whose flags nobody ever writes -- every wait on that peer must time out
+        if (!ctx->rank_mode || !ctx->detached || ctx->world < 2)
+            return fail(ctx, NB200_ESTATE, "debug_fake_peer needs a detached rank context (world > 1, no unique id)");
+        Shard& s = ctx->shards[0];
+        s.n_peers = 1;
+        s.peer_rank[0] = (s.rank + 1) % ctx->world;
+        s.peer_src[0][0] = s.src[0];
+        s.peer_src[1][0] = s.src[1];
+        s.peer_flags[0] = s.flags;
+        ctx->detached = false;
+        ctx->p2p_ready = true;
+        ctx->exchange = 1;
+    }
     else if (!strcmp(key, "sym_block")) ctx->opt_sym_block = (value == 128 || value == 256) ? (int)value : 0;
     else if (!strcmp(key, "sym_algo")) ctx->opt_sym_algo = (value >= 0 && value <= 2) ? (int)value : -1;
     else if (!strcmp(key, "sym_itile")) ctx->opt_sym_itile = value == 256 ? 256 : value == 1024 ? 1024 : 0;
@@ -1219,6 +1286,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
 
 int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
     if (!ctx) return NB200_EINVAL;
+    if (ctx->dead) return fail(ctx, NB200_ESTATE, "context is unusable after a peer handshake timeout: destroy it");
     const int D = ctx->dim;
     const size_t min_stride = (size_t)(2 * D + 1) * sizeof(double);
     if (ctx->n && !bodies) return fail(ctx, NB200_EINVAL, "null bodies");
@@ -1240,6 +1308,7 @@ int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
 
 int nb200_generate(nb200_ctx* ctx, int kind, unsigned long long seed, double G) {
     if (!ctx) return NB200_EINVAL;
+    if (ctx->dead) return fail(ctx, NB200_ESTATE, "context is unusable after a peer handshake timeout: destroy it");
     const int D = ctx->dim;
     if (kind < 0 || kind > 2) return fail(ctx, NB200_EINVAL, "generator kind %d: 0 reference range, 1 uniform cube, 2 Plummer", kind);
     if (kind == 2 && D != 3) return fail(ctx, NB200_EINVAL, "the Plummer generator is 3D only");
@@ -1309,6 +1378,7 @@ static inline double effective_cutoff(double c) { return c > 1e-20 ? c : 1e-20; 
 
 int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out) {
     if (!ctx) return NB200_EINVAL;
+    if (ctx->dead) return fail(ctx, NB200_ESTATE, "context is unusable after a peer handshake timeout: destroy it");
     cutoff_r2 = effective_cutoff(cutoff_r2);
     if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "forces before upload");
     if (ctx->n && !forces_out) return fail(ctx, NB200_EINVAL, "null forces_out");
@@ -1345,6 +1415,7 @@ int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out)
 
 int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps) {
     if (!ctx) return NB200_EINVAL;
+    if (ctx->dead) return fail(ctx, NB200_ESTATE, "context is unusable after a peer handshake timeout: destroy it");
     cutoff_r2 = effective_cutoff(cutoff_r2);
     if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "step before upload");
     if (nsteps < 0) return fail(ctx, NB200_EINVAL, "nsteps < 0");
@@ -1404,7 +1475,8 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
                 if (use_nccl) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
                 if (p2p && s.n_peers > 0 && (hs_remote.wait_step | hs_remote.wait_epoch)) {
                     nb_wait_flags_kernel<<<1, 32, 0, s.compute>>>(s.flags, kMaxWorldP2P, s.n_peers, PeerRanks(s),
-                                                                  hs_remote.wait_step, hs_remote.wait_epoch);
+                                                                  hs_remote.wait_step, hs_remote.wait_epoch,
+                                                                  (unsigned long long)std::max(1L, ctx->opt_spin_timeout_ms) * 1000000ull, s.err_dev);
                     CK(cudaGetLastError());
                     ctx->launches++;
                 }
@@ -1468,7 +1540,8 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
         if (p2p && nsteps > 0 && s.n_peers > 0) {
             // the call returns (and its device time ends) only when every peer has published the last
             // step: our source buffer is complete and no peer store into it is still in flight
-            nb_wait_flags_kernel<<<1, 32, 0, s.compute>>>(s.flags, kMaxWorldP2P, s.n_peers, PeerRanks(s), ctx->step_index, 0ull);
+            nb_wait_flags_kernel<<<1, 32, 0, s.compute>>>(s.flags, kMaxWorldP2P, s.n_peers, PeerRanks(s), ctx->step_index, 0ull,
+                                                          (unsigned long long)std::max(1L, ctx->opt_spin_timeout_ms) * 1000000ull, s.err_dev);
             CK(cudaGetLastError());
             ctx->launches++;
             trace_mark(ctx, s, s.compute, "W<", nsteps - 1);

@@ -57,7 +57,17 @@ struct NbForceParams {
     unsigned long long wait_epoch;                    // peers must have finished this many uploads (repacks)
     unsigned long long signal_step;                   // 0 = this pass publishes nothing
     int flag_stride;                                  // epoch flags live at my_flags[flag_stride + rank]
+    // every wait on a peer's flag is bounded: after spin_timeout_ns the waiter records WHAT it waited for in
+    // *err_word (page-locked host memory the host reads after the stream sync) and moves on, so a crashed or
+    // diverged peer costs an error return (NB200_ESTATE), not a hung GPU
+    unsigned long long* err_word;
+    unsigned long long spin_timeout_ns;
 };
+
+// what a timed-out wait records: kind << 56 | peer rank << 48 | awaited value (low 48 bits)
+#define NB_WAIT_STEP 1ull
+#define NB_WAIT_EPOCH 2ull
+#define NB_WAIT_REACTION 3ull
 
 // ------------------------------------------------------------------ mbarrier / TMA (sm_90+ PTX)
 __device__ __forceinline__ uint32_t nb_smem_u32(const void* p) {
@@ -108,6 +118,34 @@ __device__ __forceinline__ unsigned long long nb_ld_acquire_sys(const unsigned l
 }
 __device__ __forceinline__ void nb_st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long nb_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *flag >= want (acquire, system scope), at most timeout_ns.  Returns false on timeout after
+// recording (kind, peer, want) in *err_word.
+__device__ __forceinline__ bool nb_wait_flag(const unsigned long long* flag, unsigned long long want,
+                                             unsigned long long timeout_ns, unsigned long long* err_word,
+                                             unsigned long long kind, int peer) {
+    if (nb_ld_acquire_sys(flag) >= want) return true;
+    const unsigned long long t0 = nb_globaltimer_ns();
+    unsigned ns = 128;
+    while (nb_ld_acquire_sys(flag) < want) {
+        __nanosleep(ns);
+        if (ns < 4096) ns <<= 1;
+        if (nb_globaltimer_ns() - t0 > timeout_ns) {
+            if (err_word) {
+                *reinterpret_cast<volatile unsigned long long*>(err_word) =
+                    (kind << 56) | ((unsigned long long)(peer & 0xff) << 48) | (want & 0xffffffffffffull);
+                __threadfence_system();
+            }
+            return false;
+        }
+    }
+    return true;
 }
 
 __device__ __forceinline__ float nb_rcp_f32(float x) {

@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
     auto peer_handshake = [&]() {
         if (tid < P.n_peers) {
             const unsigned long long* f = P.my_flags + P.peer_rank[tid];
-            while (nb_ld_acquire_sys(f) < P.wait_step) __nanosleep(200);
-            while (nb_ld_acquire_sys(f + P.flag_stride) < P.wait_epoch) __nanosleep(200);
+            nb_wait_flag(f, P.wait_step, P.spin_timeout_ns, P.err_word, NB_WAIT_STEP, P.peer_rank[tid]) &&
+                nb_wait_flag(f + P.flag_stride, P.wait_epoch, P.spin_timeout_ns, P.err_word, NB_WAIT_EPOCH, P.peer_rank[tid]);
         }
         __syncthreads();
     };

@@ -98,6 +98,7 @@ struct NbSymFinish {
     int n_src;                   // senders whose slots must be added
     const double* slot[4];       // local receive slots [3][count]
     const unsigned long long* flag[4];   // local flag words of (sender -> this rank)
+    int sender[4];               // their ranks (for the timeout report)
     unsigned long long seq;      // 0 = nothing to wait for
     int count;
     unsigned* done;              // CTA completion counter for the step signal (self-resetting)
@@ -815,7 +816,7 @@ __global__ void __launch_bounds__(256) nb_finish_kernel(const NbForceParams P, c
     constexpr int NP = D + 1;
     if (F.seq != 0ull && F.n_src > 0) {
         if (threadIdx.x < F.n_src)
-            while (nb_ld_acquire_sys(F.flag[threadIdx.x]) < F.seq) __nanosleep(200);
+            nb_wait_flag(F.flag[threadIdx.x], F.seq, P.spin_timeout_ns, P.err_word, NB_WAIT_REACTION, F.sender[threadIdx.x]);
         __syncthreads();
     }
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
