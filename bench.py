@@ -35,6 +35,7 @@ import numpy as np
 # rank 0 prints exactly ONE JSON line on stdout.  Without a caller-set NCCL_DEBUG keep NCCL quiet; a caller that
 # asks for INFO (the driver's communicator check) gets it untouched.
 os.environ.setdefault("NCCL_DEBUG", "WARN")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # banner and communicator lines go to stderr, never into the JSON line
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

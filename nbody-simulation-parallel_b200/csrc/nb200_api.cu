@@ -168,6 +168,7 @@ struct Shard {
     std::vector<NbSymRow> sym_rows_host;
     std::vector<int> sym_prefix_host;
     int sym_key_seg = 0, sym_key_world = 0, sym_key_tpi = 0;
+    int sym_plan_key = -1, sym_plan_shape[2] = {0, 0}, sym_plan_seg = 0;   // cached small-problem plan (shape, unit length)
     double* gacc = nullptr;                           // [3][nalloc]
     unsigned* sym_done = nullptr;                     // [2] push / finish CTA counters
     // fused NVLink exchange (peer stores from the epilogue + flag handshake)
@@ -220,7 +221,7 @@ struct nb200_ctx {
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     bool dead = false;            // a peer handshake timed out: the ranks' step counters may have diverged
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0, opt_seg_sub = 0;
     long opt_spin_timeout_ms = 30000;   // bound of every device-side wait on a peer's flag
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
@@ -628,8 +629,13 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
 // shards (fused NVLink exchange attached): rank g also evaluates the blocks (g, g+off) for
 // off = 1 .. floor((G-1)/2) and, for even G, half of the block against the opposite rank; the
 // reaction sums on the other rank's bodies are pushed into that rank's receive slots.
+// From kSymMinN bodies up the pair-symmetric pass wins even without the close-pair pre-pass (exact cut-off on every
+// pair, ~10 % slower than the plain chains, but 7.5 instead of 11 FMA-pipe lane-ops per interaction and no extra launches)
+constexpr size_t kSymMinN = 12288;
 bool use_symmetric(const nb200_ctx* ctx, bool stepping) {
-    if (!use_detect(ctx) || ctx->opt_symmetric == 0) return false;
+    if (ctx->opt_symmetric == 0) return false;
+    if (ctx->opt_symmetric < 0 && !use_detect(ctx) && ctx->n < kSymMinN) return false;
+    if (ctx->opt_symmetric > 0 && !use_detect(ctx) && ctx->opt_detect != 0 && ctx->n < kSymMinN) return false;   // explicit 1 keeps meaning "when the pre-pass runs" below the threshold
     if (ctx->world == 1) return true;
     // cross-rank flavour: only inside nb200_step (nb200_forces stays a rank-local call)
     return stepping && !ctx->detached && ctx->p2p_ready && ctx->exchange == 1 && ctx->world <= kMaxWorldP2P;
@@ -679,17 +685,46 @@ void sym_rows_for(int g, int G, int T, std::vector<NbSymRow>& rows, int tpi = NB
     }
 }
 
-int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg, bool cross, int tpi) {
+// units of one row: symmetric rows are cut every seg_sub sub-tiles (subt per tile), ordered rows every seg_ord tiles
+int sym_row_units(const NbSymRow& r, int subt, int seg_sub, int seg_ord) {
+    const int len = r.t_end - r.t_begin;
+    return (r.flags & NB_ROW_SYM) ? (len * subt + seg_sub - 1) / seg_sub : (len + seg_ord - 1) / seg_ord;
+}
+
+// Completion time (in symmetric-tile units) of the work list under the kernel's dynamic scheduler: units are
+// handed out in flat order to whichever of the C resident CTAs frees first.  c0 = fixed cost of a unit (target
+// loads, first TMA wait, the FP64 atomics of the target sums); an ordered tile costs 11/15 of a symmetric one.
+double sym_makespan(const std::vector<NbSymRow>& rows, int subt, int seg_sub, int seg_ord, int C, double c0) {
+    std::vector<double> heap((size_t)C, 0.0);           // min-heap of CTA finish times
+    auto cmp = [](double x, double y) { return x > y; };
+    double last = 0.0;
+    for (const NbSymRow& r : rows) {
+        const bool sym = (r.flags & NB_ROW_SYM) != 0;
+        const int len = (r.t_end - r.t_begin) * (sym ? subt : 1), seg = sym ? seg_sub : seg_ord;
+        for (int b = 0; b < len; b += seg) {
+            const int l = std::min(seg, len - b);
+            const double cost = c0 + (sym ? (double)l / subt : l * (11.0 / 15.0));
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            heap.back() += cost;
+            last = std::max(last, heap.back());
+            std::push_heap(heap.begin(), heap.end(), cmp);
+        }
+    }
+    return last;
+}
+
+int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg_sub, int seg_ord, int subt, bool cross, int tpi) {
     const int G = cross ? ctx->world : 1;
-    if (!s.sym_rows_host.empty() && s.sym_key_seg == seg && s.sym_key_world == G && s.sym_key_tpi == tpi) return NB200_OK;
+    const int key_seg = seg_sub * 4096 + seg_ord * 8 + subt;
+    if (!s.sym_rows_host.empty() && s.sym_key_seg == key_seg && s.sym_key_world == G && s.sym_key_tpi == tpi) return NB200_OK;
     std::vector<NbSymRow>& rows = s.sym_rows_host;
     sym_rows_for(cross ? s.rank : 0, G, (int)ctx->tiles_per_shard, rows, tpi);
     s.sym_key_tpi = tpi;
     if ((int)rows.size() > s.sym_rows_cap) return fail(ctx, NB200_ESTATE, "symmetric work list overflow");
     s.sym_prefix_host.assign(rows.size() + 1, 0);
     for (size_t r = 0; r < rows.size(); ++r)
-        s.sym_prefix_host[r + 1] = s.sym_prefix_host[r] + (rows[r].t_end - rows[r].t_begin + seg - 1) / seg;
-    s.sym_key_seg = seg;
+        s.sym_prefix_host[r + 1] = s.sym_prefix_host[r] + sym_row_units(rows[r], subt, seg_sub, seg_ord);
+    s.sym_key_seg = key_seg;
     s.sym_key_world = G;
     CK(cudaMemcpyAsync(s.sym_rows, rows.data(), rows.size() * sizeof(NbSymRow), cudaMemcpyHostToDevice, s.compute));
     CK(cudaMemcpyAsync(s.sym_prefix, s.sym_prefix_host.data(), s.sym_prefix_host.size() * sizeof(int),
@@ -698,7 +733,7 @@ int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg, bool cross, int tpi) {
 }
 
 // symmetric force kernel, [push of the reaction sums to their owners], finish kernel (forces or integrate)
-int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff, double dt, int cur,
+int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff, double dt, int cur, bool with_flags,
                      const Handshake& hs = Handshake()) {
     const int D = ctx->dim;
     const bool cross = ctx->world > 1;
@@ -720,23 +755,59 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
             sh.block = sh.ti == 8 ? 128 : ctx->opt_sym_block == 128 ? 128 : 256;
         }
     }
+    const int algo = small ? 0 : std::min(ctx->opt_sym_algo >= 0 ? ctx->opt_sym_algo : kSymAlgoDefault, ctx->f64 ? 1 : 2);
+    const int subt = nb_sym_subtiles(ctx->f64, algo);
+    // work units: ~32 per resident CTA keep the tail short; a small problem cannot afford that many (a unit pays a
+    // fixed start-up), so there the unit length -- and, for FP32, the shape -- is picked by simulating the kernel's
+    // own dynamic scheduler on the work list (cached per shard)
+    auto resident_of = [&](SymShape c, int* out) -> cudaError_t {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)pick_sym_kernel(D, ctx->f64, c, algo), c.block,
+                                                                      nb_sym_smem_bytes(D, c.block, ctx->f64, c.ti, algo));
+        *out = std::max(1, nb) * s.sms;
+        return e;
+    };
+    int resident = 0;
+    CK(resident_of(sh, &resident));
+    int seg_sub = ctx->opt_seg_sub > 0 ? ctx->opt_seg_sub : ctx->opt_seg_tiles * subt;
+    if (seg_sub <= 0) {
+        const long long n_it0 = ((long long)tiles * NB_TILE + sh.ti * sh.block - 1) / (sh.ti * sh.block);
+        const long long cells = n_it0 * (long long)ctx->ntiles / 2;     // (i-tile, source tile) cells this rank evaluates
+        if (cells >= 64LL * resident || small) {
+            seg_sub = subt * (int)std::max<long long>(small ? 1 : 2, std::min<long long>(32, cells / (32LL * resident)));
+        } else {
+            const bool key_hit = s.sym_plan_key == (int)(ctx->opt_sym_ti * 1000 + ctx->opt_sym_block + algo * 100000 + (cross ? W : 1) * 1000000);
+            if (!key_hit) {
+                std::vector<SymShape> cands{sh};
+                if (!ctx->f64 && !ctx->opt_sym_ti && !ctx->opt_sym_block) cands = {{8, 128}, {4, 128}};
+                double best = 1e300;
+                std::vector<NbSymRow> rows;
+                for (const SymShape& c : cands) {
+                    int res_c = 0;
+                    CK(resident_of(c, &res_c));
+                    const int it_c = c.ti * c.block;
+                    sym_rows_for(cross ? s.rank : 0, cross ? W : 1, tiles, rows, it_c / NB_TILE);
+                    // measured pair rates of the shapes at large N (profiles/r02): 8x128 3864, 4x128 3706, 4x256 3811 G inter/s
+                    const double rate = c.ti == 8 ? 3864.0 : c.block == 128 ? 3706.0 : 3811.0;
+                    for (int sgs : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32}) {
+                        const double t = sym_makespan(rows, subt, sgs, std::max(1, sgs / subt), res_c, 0.08) * it_c * res_c / rate;
+                        if (t < best) { best = t; s.sym_plan_shape[0] = c.ti; s.sym_plan_shape[1] = c.block; s.sym_plan_seg = sgs; }
+                    }
+                }
+                s.sym_plan_key = (int)(ctx->opt_sym_ti * 1000 + ctx->opt_sym_block + algo * 100000 + (cross ? W : 1) * 1000000);
+            }
+            sh = SymShape{s.sym_plan_shape[0], s.sym_plan_shape[1]};
+            seg_sub = s.sym_plan_seg;
+            CK(resident_of(sh, &resident));
+        }
+    }
     const int ti = sh.ti, block = sh.block;
     const int itile = ti * block;
-    const int algo = small ? 0 : std::min(ctx->opt_sym_algo >= 0 ? ctx->opt_sym_algo : kSymAlgoDefault, ctx->f64 ? 1 : 2);
+    const int seg_ord = std::max(1, seg_sub / subt);
     const SymKernel kfn = pick_sym_kernel(D, ctx->f64, sh, algo);
     const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64, ti, algo);
-    int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kfn, block, smem));
-    const int resident = std::max(1, nb) * s.sms;
-    int seg = ctx->opt_seg_tiles;
-    if (seg <= 0) {
-        // this rank evaluates ~ n_it * NT/2 (i-tile, source tile) cells: aim for ~32 units per resident CTA
-        // (tail balance) without going under 2 tiles per unit (per-unit start-up) or over 32
-        const long long n_it = ((long long)tiles * NB_TILE + itile - 1) / itile;
-        const long long cells = n_it * (long long)ctx->ntiles / 2;
-        seg = (int)std::max<long long>(small ? 1 : 2, std::min<long long>(32, cells / (32LL * resident)));
-    }
-    if (int rc = build_sym_rows(ctx, s, seg, cross, itile / NB_TILE)) return rc;
+    if (int rc = build_sym_rows(ctx, s, seg_sub, seg_ord, subt, cross, itile / NB_TILE)) return rc;
+    const int seg = seg_sub;
     NbSymParams Q;
     memset(&Q, 0, sizeof Q);
     Q.src = s.src[cur];
@@ -745,11 +816,12 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     Q.sched = s.sched;
     Q.rows = s.sym_rows;
     Q.row_prefix = s.sym_prefix;
-    Q.suspect = s.suspect;
+    Q.suspect = with_flags ? s.suspect : nullptr;      // no pre-pass: exact cut-off on every pair
     Q.tgt_base = s.tgt_base;
     Q.own_count = tiles * NB_TILE;
     Q.n_rows = (int)s.sym_rows_host.size();
-    Q.seg_tiles = seg;
+    Q.seg_sub = seg_sub;
+    Q.seg_ord = seg_ord;
     Q.total_units = s.sym_prefix_host.back();
     Q.cutoff = cutoff * ctx->pos_scale * ctx->pos_scale;
     const int grid = std::min(resident, Q.total_units);
@@ -811,10 +883,11 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     if (&s == &ctx->shards[0]) {
         char buf[320];
         snprintf(buf, sizeof buf,
-                 "%s: fp%d dim=%d n=%zu shards=%d pair-symmetric(TI=%d,block=%d,itile=%d) seg_tiles=%d rows=%d "
-                 "units=%d grid=%d tiles=%lld cutoff=grid-prepass(plain|exact)%s + finish kernel",
-                 mode ? "step" : "forces", ctx->f64 ? 64 : 32, D, ctx->n, ctx->world, ti, block, itile, seg, Q.n_rows, Q.total_units, grid,
-                 ctx->ntiles, cross ? " + reaction sums pushed to their owners over NVLink" : "");
+                 "%s: fp%d dim=%d n=%zu shards=%d pair-symmetric(TI=%d,block=%d,itile=%d) algo=%d seg=%d/%d tiles rows=%d "
+                 "units=%d grid=%d tiles=%lld cutoff=%s%s + finish kernel",
+                 mode ? "step" : "forces", ctx->f64 ? 64 : 32, D, ctx->n, ctx->world, ti, block, itile, algo, seg, subt, Q.n_rows, Q.total_units, grid,
+                 ctx->ntiles, with_flags ? "grid-prepass(plain|exact)" : "exact",
+                 cross ? " + reaction sums pushed to their owners over NVLink" : "");
         ctx->plan = buf;
     }
     return NB200_OK;
@@ -1249,6 +1322,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     if (!ctx || !key) return NB200_EINVAL;
     if (!strcmp(key, "variant")) ctx->opt_variant = (value >= 0 && value < kNumVariants) ? (int)value : -1;
     else if (!strcmp(key, "seg_tiles")) ctx->opt_seg_tiles = (int)std::max(0L, value);
+    else if (!strcmp(key, "seg_sub")) ctx->opt_seg_sub = (int)std::max(0L, value);
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);
     else if (!strcmp(key, "overlap")) ctx->opt_overlap = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "trace")) ctx->opt_trace = value != 0;
@@ -1394,7 +1468,7 @@ int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out)
         CK(cudaEventRecord(s.ev_start, s.compute));
         if (pl.flags) { if (int rcd = launch_detect(ctx, s, cutoff_r2, ctx->cur)) return rcd; }
         if (use_symmetric(ctx, false)) {
-            rc = launch_symmetric(ctx, s, 0, G, cutoff_r2, 0.0, ctx->cur);
+            rc = launch_symmetric(ctx, s, 0, G, cutoff_r2, 0.0, ctx->cur, pl.flags);
         } else {
             Ranges all(0, (int)ctx->ntiles);
             rc = launch_pass(ctx, s, pl, all, (unsigned)total_units_per_itile(ctx, s, pl, false), 0, G, cutoff_r2, 0.0, ctx->cur);
@@ -1470,8 +1544,10 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
             CK(cudaSetDevice(s.device));
             const unsigned upi = (unsigned)total_units_per_itile(ctx, s, pl, split);
             int rc;
-            if (pl.flags) {
-                // the pre-pass reads every source row of this step: take the exchange handshake first
+            const bool symmetric = use_symmetric(ctx, true);
+            if (pl.flags || symmetric) {
+                // the pre-pass and the pair-symmetric pass read every source row of this step: take the exchange
+                // handshake first
                 if (use_nccl) CK(cudaStreamWaitEvent(s.compute, s.ev_gather[cur], 0));
                 if (p2p && s.n_peers > 0 && (hs_remote.wait_step | hs_remote.wait_epoch)) {
                     nb_wait_flags_kernel<<<1, 32, 0, s.compute>>>(s.flags, kMaxWorldP2P, s.n_peers, PeerRanks(s),
@@ -1480,11 +1556,13 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
                     CK(cudaGetLastError());
                     ctx->launches++;
                 }
-                rc = launch_detect(ctx, s, cutoff_r2, cur);
-                if (rc) return rc;
+                if (pl.flags) {
+                    rc = launch_detect(ctx, s, cutoff_r2, cur);
+                    if (rc) return rc;
+                }
             }
-            if (use_symmetric(ctx, true)) {
-                rc = launch_symmetric(ctx, s, 1, G, cutoff_r2, dt, cur, hs_remote);
+            if (symmetric) {
+                rc = launch_symmetric(ctx, s, 1, G, cutoff_r2, dt, cur, pl.flags, hs_remote);
             } else if (split && use_nccl) {
                 // two launches around the all-gather event: own sources, then the other shards'
                 Ranges own((int)s.tile_lo, (int)s.tile_hi);

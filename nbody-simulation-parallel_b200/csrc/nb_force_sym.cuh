@@ -43,6 +43,9 @@ struct NbSymRow {
 };
 #define NB_ROW_SYM 1
 
+// sub-tiles per source tile a symmetric row's units are measured in
+__host__ __device__ constexpr int nb_sym_subtiles(bool f64, int algo) { return algo == 0 ? 1 : f64 ? 4 : 2; }
+
 // compile-time experiments of the rotation flavour (csrc/Makefile EXTRA=-D...)
 #ifndef NB_ROT_UNROLL
 #define NB_ROT_UNROLL 1
@@ -67,11 +70,13 @@ struct NbSymParams {
     unsigned* sched;             // [2] unit counter + exit counter (self-resetting)
     const NbSymRow* rows;        // [n_rows]
     const int* row_prefix;       // [n_rows + 1] first flat unit index of every row
-    const unsigned char* suspect;   // [tpad] close-pair flags of the own targets
+    const unsigned char* suspect;   // [tpad] close-pair flags of the own targets; null = no pre-pass ran: exact cut-off everywhere
     long long tgt_base;          // first own body (multiple of NB_TILE)
     int own_count;               // bodies of this shard incl. tile padding; targets past it are inert
     int n_rows;
-    int seg_tiles;               // source tiles per unit
+    int seg_sub;                 // SYMMETRIC rows: sub-tiles per unit (a tile = SUBT sub-tiles: 1 transpose flavour,
+                                 // 2 FP32 rotation (128 sources), 4 FP64 rotation (64 sources))
+    int seg_ord;                 // ORDERED rows: source tiles per unit
     int total_units;
     double cutoff;               // r^2 cut-off in source units
 };
@@ -254,7 +259,8 @@ template <int D, int TI, int MODE, bool DECOUPLE>
 __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ stage, float cutoff,
                                                     const float (&npos)[TI][3],
                                                     const float (&mi)[TI],
-                                                    float2 (&a)[TI][3], float* __restrict__ wout, int lane) {
+                                                    float2 (&a)[TI][3], float* __restrict__ wout, int lane,
+                                                    int hf_begin, int hf_end) {
     // plane p of the stage as float2: source pair (group g, half h) sits at p * (NB_TILE / 2) + 2 g + h
     const float2* sx = reinterpret_cast<const float2*>(stage);
     const float2* sy = sx + NB_TILE / 2;
@@ -331,7 +337,7 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
     const float2 zero2 = make_float2(0.f, 0.f);
 
 #pragma unroll 1
-    for (int hf = 0; hf < NB_TILE / 128; ++hf) {
+    for (int hf = hf_begin; hf < hf_end; ++hf) {
         float2 trav[2][3];                                    // travelling sums of the group this lane meets next
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -485,14 +491,15 @@ __device__ __forceinline__ void nb_tile_f64_sym(const double* __restrict__ stage
 template <int D, int TI, bool EXACT>
 __device__ __forceinline__ void nb_tile_f64_sym_rot(const double* __restrict__ stage, double cutoff,
                                                     const double (&pos)[TI][3], const double (&mi)[TI],
-                                                    double (&accd)[TI][3], double* __restrict__ wout, int lane) {
+                                                    double (&accd)[TI][3], double* __restrict__ wout, int lane,
+                                                    int qd_begin, int qd_end) {
     const double2* sx = reinterpret_cast<const double2*>(stage);
     const double2* sy = sx + NB_TILE / 2;
     const double2* sz = sy + NB_TILE / 2;                     // D == 3 only
     const double2* sm = sx + D * (NB_TILE / 2);
     const int from = (lane + 1) & 31;
 #pragma unroll 1
-    for (int qd = 0; qd < NB_TILE / 64; ++qd) {
+    for (int qd = qd_begin; qd < qd_end; ++qd) {
         double trav[2][3];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -615,8 +622,13 @@ nb_force_sym_kernel(const NbSymParams P) {
         const NbSymRow R = P.rows[row];
         const int it = R.it;
         const bool sym = (R.flags & NB_ROW_SYM) != 0;
-        const int ts = R.t_begin + sg * P.seg_tiles;
-        const int te = min(ts + P.seg_tiles, R.t_end);
+        // a symmetric row is cut in units of seg_sub sub-tiles, an ordered row in units of seg_ord tiles
+        constexpr int SUBT = nb_sym_subtiles(F64, ALGO);
+        const int rsub = sym ? SUBT : 1;
+        const int s0 = R.t_begin * rsub + sg * (sym ? P.seg_sub : P.seg_ord);
+        const int s1 = min(s0 + (sym ? P.seg_sub : P.seg_ord), R.t_end * rsub);
+        const int ts = s0 / rsub;
+        const int te = (s1 + rsub - 1) / rsub;
         const int ntl = te - ts;
 
         if (tid == 0) {
@@ -650,9 +662,9 @@ nb_force_sym_kernel(const NbSymParams P) {
                 tq[t][d] = F64 ? x : -x;
             }
             mi[t] = live ? tb[D * NB_TILE] : real(0);
-            suspect |= P.suspect[it * ITILE + tid + t * BLOCK] != 0;
+            if (P.suspect) suspect |= P.suspect[it * ITILE + tid + t * BLOCK] != 0;
         }
-        const bool warp_suspect = __any_sync(0xffffffffu, suspect) != 0;
+        const bool warp_suspect = !P.suspect || __any_sync(0xffffffffu, suspect) != 0;
         // FP64 sums of the own targets over the unit: in registers, or (rotation flavours, experiment) in the
         // shared memory the transpose scratch no longer needs -- 24 registers back for the chains
         constexpr bool SACC = NB_ROT_SMEM_ACC && !F64 && ALGO != 0;
@@ -683,6 +695,9 @@ nb_force_sym_kernel(const NbSymParams P) {
             nb_mbar_wait(&full_bar[slot], (k / STAGES) & 1u);
             const real* stage = ring + (size_t)slot * TILE_ELEMS;
             real* wout = bout_all + ((size_t)bbuf * NWARPS + warp) * (D * NB_TILE);
+            // sub-tiles [h0, h1) of this tile belong to the unit (whole tile: [0, SUBT))
+            const int h0 = sym ? max(s0 - (ts + t) * SUBT, 0) : 0;
+            const int h1 = sym ? min(s1 - (ts + t) * SUBT, SUBT) : SUBT;
             bool exact_tile = warp_suspect;
             if (!sym) {
 #pragma unroll
@@ -700,8 +715,8 @@ nb_force_sym_kernel(const NbSymParams P) {
                         if (exact_tile) nb_tile_f64_sym<D, TI, true>(dstage, P.cutoff, pos, mid, accd, dscr, dwout, lane);
                         else nb_tile_f64_sym<D, TI, false>(dstage, P.cutoff, pos, mid, accd, dscr, dwout, lane);
                     } else {
-                        if (exact_tile) nb_tile_f64_sym_rot<D, TI, true>(dstage, P.cutoff, pos, mid, accd, dwout, lane);
-                        else nb_tile_f64_sym_rot<D, TI, false>(dstage, P.cutoff, pos, mid, accd, dwout, lane);
+                        if (exact_tile) nb_tile_f64_sym_rot<D, TI, true>(dstage, P.cutoff, pos, mid, accd, dwout, lane, h0, h1);
+                        else nb_tile_f64_sym_rot<D, TI, false>(dstage, P.cutoff, pos, mid, accd, dwout, lane, h0, h1);
                     }
                 } else {
                     if (exact_tile) nb_tile_f64<D, TI, 1, true>(dstage, 0, P.cutoff, pos, accd);
@@ -719,8 +734,8 @@ nb_force_sym_kernel(const NbSymParams P) {
                         if (exact_tile) nb_tile_f32_sym<D, TI, NB_EXACT>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
                         else nb_tile_f32_sym<D, TI, NB_PLAIN>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
                     } else {
-                        if (exact_tile) nb_tile_f32_sym_rot<D, TI, NB_EXACT, ALGO == 2>(fstage, cutoff_f, npos, mif, a, fwout, lane);
-                        else nb_tile_f32_sym_rot<D, TI, NB_PLAIN, ALGO == 2>(fstage, cutoff_f, npos, mif, a, fwout, lane);
+                        if (exact_tile) nb_tile_f32_sym_rot<D, TI, NB_EXACT, ALGO == 2>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1);
+                        else nb_tile_f32_sym_rot<D, TI, NB_PLAIN, ALGO == 2>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1);
                     }
                 } else {
                     if (exact_tile) nb_tile_f32<D, TI, 1, NB_EXACT, 1>(fstage, 0, cutoff_f, npos, a);
@@ -741,7 +756,7 @@ nb_force_sym_kernel(const NbSymParams P) {
                 // the reaction on source j is MINUS sum_i (m_i / r^4) d_ij
                 __syncthreads();
                 const real* bb = bout_all + (size_t)bbuf * NWARPS * (D * NB_TILE);
-                for (int j = tid; j < NB_TILE; j += BLOCK) {
+                for (int j = h0 * (NB_TILE / SUBT) + tid; j < h1 * (NB_TILE / SUBT); j += BLOCK) {
                     const size_t gj = (size_t)(ts + t) * NB_TILE + j;
 #pragma unroll
                     for (int d = 0; d < D; ++d) {

@@ -631,6 +631,40 @@ def test_pair_symmetric_fp64_shapes(pkg, oracle, dim, n, algo, sym_ti, block, se
     assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= 1e-12 * scale
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("n,seg_sub,detect,shape", [(5000, 1, 1, (0, 0)), (5000, 3, 0, (0, 0)), (13000, 0, 0, (0, 0)),
+                                                    (13000, 1, 0, (4, 128)), (9473, 5, 0, (4, 256)), (20000, 0, -1, (0, 0))])
+def test_pair_symmetric_subtile_units_and_no_prepass(pkg, oracle, dim, prec, n, seg_sub, detect, shape):
+    """Work units of the rotation flavours end on sub-tile boundaries (128 sources FP32, 64 FP64), and without
+    the close-pair pre-pass (detect=0, the default for 12288 <= N < 32768) every pair takes the exact cut-off:
+    duplicates and pairs under the cut-off included, against the oracle and the ordered pass."""
+    b = pkg.generators.uniform_cube(n, dim, seed=500 + n)
+    b[17, :dim] = b[3, :dim]
+    b[101, :dim] = b[100, :dim] + 2e-6
+    b[n - 1, :dim] = b[n - 300, :dim] + 3e-6
+    if prec == 32:
+        b = pkg.generators.round_to_float(b)
+    opts = {"symmetric": 1, "detect": detect, "seg_sub": seg_sub}
+    if shape[0] and prec == 32:
+        opts.update(sym_ti=shape[0], sym_block=shape[1])
+    with pkg.NBodyCuda(dim, n, prec) as ctx:
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        ctx.upload(b)
+        f = ctx.forces()
+        assert "pair-symmetric" in ctx.plan, ctx.plan
+        assert ("cutoff=exact" in ctx.plan) == (detect == 0 or (detect < 0 and n < 32768)), ctx.plan
+    if prec == 32:
+        assert_fp32_parity(pkg, oracle, f, b, f"n={n} seg_sub={seg_sub} detect={detect}")
+    else:
+        assert rel(pkg, f, oracle.forces(b)).max() <= TOL64
+    got = pkg.brute_force_cuda_simulate(b, 1e-5, 3, prec, options=opts)
+    want = pkg.brute_force_cuda_simulate(b, 1e-5, 3, prec, options={"symmetric": 0})
+    scale = np.abs(want[:, :2 * dim]).max()
+    assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= (2e-6 if prec == 32 else 1e-12) * scale
+
+
 # ------------------------------------------------------------------ -a 1 column and validation print on the device
 @pytest.mark.parametrize("dim,n", [(3, 3001), (2, 1000), (3, 5)])
 def test_device_side_accuracy_and_validation_forces(pkg, oracle, dim, n):
