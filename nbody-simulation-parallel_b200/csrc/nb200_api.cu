@@ -168,7 +168,6 @@ struct Shard {
     std::vector<NbSymRow> sym_rows_host;
     std::vector<int> sym_prefix_host;
     int sym_key_seg = 0, sym_key_world = 0, sym_key_tpi = 0;
-    int sym_plan_key = -1, sym_plan_shape[2] = {0, 0}, sym_plan_seg = 0;   // cached small-problem plan (shape, unit length)
     double* gacc = nullptr;                           // [3][nalloc]
     unsigned* sym_done = nullptr;                     // [2] push / finish CTA counters
     // fused NVLink exchange (peer stores from the epilogue + flag handshake)
@@ -191,7 +190,7 @@ constexpr size_t kSymSmallN = 0;
 // Reaction-sum reduction of the pair-symmetric kernel: 0 shared-memory transpose, 1 register rotation through the
 // warp, 2 (FP32) rotation with decoupled hand-over.  Measured at N = 2^20, FP32 3D: 3323 / 3811 / 3757 G inter/s
 // with 4 x 256 threads, 3864 with 8 x 128 and rotation (profiles/r02_sym_variants.jsonl).
-constexpr int kSymAlgoDefault = 1;
+constexpr int kSymAlgoDefault = 2;     // FP64 has no flavour 2: it takes 1
 constexpr int kSymTiF32 = 8;
 constexpr int kSymTiF64 = 4;
 
@@ -429,11 +428,13 @@ struct Plan {
     bool flags;       // close-pair pre-pass + NB_PLAIN/NB_EXACT kernels instead of the tracked pass
 };
 
-// the pre-pass costs a few small launches per step; together with the pair-symmetric pass it enables, it wins
-// from N ~ 32768 up (3D FP32: 2323 vs 2245 G inter/s there, 2887 vs 2394 at 49152)
+// The close-pair pre-pass (two memsets + two small launches per step, ~70 us) lets the force kernels drop all per-pair
+// cut-off work.  Against the exact-cut-off flavour of the pair-symmetric pass (~10 % slower chains in 3D, ~15 % in 2D) it
+// pays from N ~ 50000: measured at N = 65536, FP32: 1.275 vs 1.296 ms/step in 3D, 0.944 vs 1.002 in 2D; at 32768 (3D) it
+// loses, 0.432 vs 0.351 (profiles/r02/small_n.md).
 bool use_detect(const nb200_ctx* ctx) {
     if (ctx->opt_detect >= 0) return ctx->opt_detect != 0;
-    return ctx->n >= ((ctx->f64 || ctx->dim == 2) ? 24576u : 32768u);   // FP64 / 2D: 1077 vs 974, 2953 vs 2762 at 24576
+    return ctx->n >= 49152u;
 }
 
 int make_plan(nb200_ctx* ctx, const Shard& s, Plan* out) {
@@ -691,28 +692,6 @@ int sym_row_units(const NbSymRow& r, int subt, int seg_sub, int seg_ord) {
     return (r.flags & NB_ROW_SYM) ? (len * subt + seg_sub - 1) / seg_sub : (len + seg_ord - 1) / seg_ord;
 }
 
-// Completion time (in symmetric-tile units) of the work list under the kernel's dynamic scheduler: units are
-// handed out in flat order to whichever of the C resident CTAs frees first.  c0 = fixed cost of a unit (target
-// loads, first TMA wait, the FP64 atomics of the target sums); an ordered tile costs 11/15 of a symmetric one.
-double sym_makespan(const std::vector<NbSymRow>& rows, int subt, int seg_sub, int seg_ord, int C, double c0) {
-    std::vector<double> heap((size_t)C, 0.0);           // min-heap of CTA finish times
-    auto cmp = [](double x, double y) { return x > y; };
-    double last = 0.0;
-    for (const NbSymRow& r : rows) {
-        const bool sym = (r.flags & NB_ROW_SYM) != 0;
-        const int len = (r.t_end - r.t_begin) * (sym ? subt : 1), seg = sym ? seg_sub : seg_ord;
-        for (int b = 0; b < len; b += seg) {
-            const int l = std::min(seg, len - b);
-            const double cost = c0 + (sym ? (double)l / subt : l * (11.0 / 15.0));
-            std::pop_heap(heap.begin(), heap.end(), cmp);
-            heap.back() += cost;
-            last = std::max(last, heap.back());
-            std::push_heap(heap.begin(), heap.end(), cmp);
-        }
-    }
-    return last;
-}
-
 int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg_sub, int seg_ord, int subt, bool cross, int tpi) {
     const int G = cross ? ctx->world : 1;
     const int key_seg = seg_sub * 4096 + seg_ord * 8 + subt;
@@ -757,49 +736,24 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     }
     const int algo = small ? 0 : std::min(ctx->opt_sym_algo >= 0 ? ctx->opt_sym_algo : kSymAlgoDefault, ctx->f64 ? 1 : 2);
     const int subt = nb_sym_subtiles(ctx->f64, algo);
-    // work units: ~32 per resident CTA keep the tail short; a small problem cannot afford that many (a unit pays a
-    // fixed start-up), so there the unit length -- and, for FP32, the shape -- is picked by simulating the kernel's
-    // own dynamic scheduler on the work list (cached per shard)
-    auto resident_of = [&](SymShape c, int* out) -> cudaError_t {
-        int nb = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)pick_sym_kernel(D, ctx->f64, c, algo), c.block,
-                                                                      nb_sym_smem_bytes(D, c.block, ctx->f64, c.ti, algo));
-        *out = std::max(1, nb) * s.sms;
-        return e;
-    };
+    // small FP32 problems (measured, profiles/r02/small_n.jsonl): 512-target i-tiles on five CTAs per SM balance better
+    // up to N ~ 24576 (N=16384: 0.108 ms/step vs 0.112 with 8 x 128)
+    if (!small && !ctx->f64 && !ctx->opt_sym_ti && !ctx->opt_sym_block && !cross && (long long)tiles * NB_TILE <= 24576)
+        sh = SymShape{4, 128};
     int resident = 0;
-    CK(resident_of(sh, &resident));
+    {
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)pick_sym_kernel(D, ctx->f64, sh, algo), sh.block,
+                                                         nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo)));
+        resident = std::max(1, nb) * s.sms;
+    }
+    // work units: ~18 per resident CTA keep the tail short without paying a unit's fixed cost (target loads, first TMA
+    // wait, the FP64 atomics of the target sums) too often; at most 32 tiles, at least one sub-tile
     int seg_sub = ctx->opt_seg_sub > 0 ? ctx->opt_seg_sub : ctx->opt_seg_tiles * subt;
     if (seg_sub <= 0) {
         const long long n_it0 = ((long long)tiles * NB_TILE + sh.ti * sh.block - 1) / (sh.ti * sh.block);
         const long long cells = n_it0 * (long long)ctx->ntiles / 2;     // (i-tile, source tile) cells this rank evaluates
-        if (cells >= 64LL * resident || small) {
-            seg_sub = subt * (int)std::max<long long>(small ? 1 : 2, std::min<long long>(32, cells / (32LL * resident)));
-        } else {
-            const bool key_hit = s.sym_plan_key == (int)(ctx->opt_sym_ti * 1000 + ctx->opt_sym_block + algo * 100000 + (cross ? W : 1) * 1000000);
-            if (!key_hit) {
-                std::vector<SymShape> cands{sh};
-                if (!ctx->f64 && !ctx->opt_sym_ti && !ctx->opt_sym_block) cands = {{8, 128}, {4, 128}};
-                double best = 1e300;
-                std::vector<NbSymRow> rows;
-                for (const SymShape& c : cands) {
-                    int res_c = 0;
-                    CK(resident_of(c, &res_c));
-                    const int it_c = c.ti * c.block;
-                    sym_rows_for(cross ? s.rank : 0, cross ? W : 1, tiles, rows, it_c / NB_TILE);
-                    // measured pair rates of the shapes at large N (profiles/r02): 8x128 3864, 4x128 3706, 4x256 3811 G inter/s
-                    const double rate = c.ti == 8 ? 3864.0 : c.block == 128 ? 3706.0 : 3811.0;
-                    for (int sgs : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32}) {
-                        const double t = sym_makespan(rows, subt, sgs, std::max(1, sgs / subt), res_c, 0.08) * it_c * res_c / rate;
-                        if (t < best) { best = t; s.sym_plan_shape[0] = c.ti; s.sym_plan_shape[1] = c.block; s.sym_plan_seg = sgs; }
-                    }
-                }
-                s.sym_plan_key = (int)(ctx->opt_sym_ti * 1000 + ctx->opt_sym_block + algo * 100000 + (cross ? W : 1) * 1000000);
-            }
-            sh = SymShape{s.sym_plan_shape[0], s.sym_plan_shape[1]};
-            seg_sub = s.sym_plan_seg;
-            CK(resident_of(sh, &resident));
-        }
+        seg_sub = (int)std::max<long long>(1, std::min<long long>(32LL * subt, cells * subt / (18LL * resident)));
     }
     const int ti = sh.ti, block = sh.block;
     const int itile = ti * block;
