@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256) nb_accuracy_kernel(const double* __restri
 #define NB_CMP_BINS 19
 template <int D>
 __global__ void __launch_bounds__(256) nb_compare_kernel(const double* __restrict__ fa, const double* __restrict__ fb,
-                                                          long long n, long long index_base,
+                                                          long long n, long long index_base, int pass,
                                                           unsigned long long* __restrict__ out) {
     __shared__ unsigned hist[NB_CMP_BINS];
     if (threadIdx.x < NB_CMP_BINS) hist[threadIdx.x] = 0u;
@@ -364,19 +364,21 @@ __global__ void __launch_bounds__(256) nb_compare_kernel(const double* __restric
             den = fma(b, b, den);
         }
         const double rel = (num == 0.0) ? 0.0 : sqrt(num / den);      // den = 0 with num > 0: inf
-        int bin;
-        if (!isfinite(rel)) bin = NB_CMP_BINS - 1;
-        else if (rel < 1e-16) bin = 0;
-        else bin = min(NB_CMP_BINS - 2, max(1, (int)floor(log10(rel)) + 17));
-        atomicAdd(&hist[bin], 1u);
-        if (isfinite(rel)) {
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(rel);
-            const unsigned long long old = atomicMax(&out[0], bits);
-            if (bits > old) out[1] = (unsigned long long)(index_base + i);   // racy between equal maxima only: any of them
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(rel);
+        if (pass == 0) {
+            int bin;
+            if (!isfinite(rel)) bin = NB_CMP_BINS - 1;
+            else if (rel < 1e-16) bin = 0;
+            else bin = min(NB_CMP_BINS - 2, max(1, (int)floor(log10(rel)) + 17));
+            atomicAdd(&hist[bin], 1u);
+            if (isfinite(rel)) atomicMax(&out[0], bits);
+        } else if (isfinite(rel) && bits == out[0]) {
+            atomicMin(&out[1], (unsigned long long)(index_base + i));     // pass 1: the first body that attains the maximum
         }
     }
     __syncthreads();
-    if (threadIdx.x < NB_CMP_BINS && hist[threadIdx.x]) atomicAdd(&out[2 + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+    if (pass == 0 && threadIdx.x < NB_CMP_BINS && hist[threadIdx.x])
+        atomicAdd(&out[2 + threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------

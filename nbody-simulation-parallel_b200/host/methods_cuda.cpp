@@ -3,6 +3,8 @@
 // definitions + explicit instantiations for D = 2, 3: methods.cpp:453-466, :495-499).
 #include "methods_cuda.h"
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -25,7 +27,10 @@ struct Session {
     int precision = 0;
     int gpus = 0;
     double last_ms = 0.0;
-    ~Session() { reset(); }
+    // No destructor: this object is a function-local static, so its destructor would run after the CUDA runtime's
+    // own atexit teardown and free device memory / destroy NCCL communicators through a dead runtime.  At process
+    // exit the context is simply left to the OS; brute_force_cuda_release() tears it down explicitly (the patched
+    // main.cpp calls it before returning).
     void reset() {
         if (ctx) nb200_destroy(ctx);
         ctx = nullptr;
@@ -45,6 +50,26 @@ int env_int(const char* name, int fallback) {
     const char* v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : fallback;
 }
+
+// NB200_TRACE=1: host wall-clock of every phase of a call on stderr (context, upload, compute, download)
+struct PhaseTrace {
+    bool on = env_int("NB200_TRACE", 0) != 0;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    std::string line;
+    void mark(const char* name) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        char buf[64];
+        std::snprintf(buf, sizeof buf, " %s=%.3fms", name, std::chrono::duration<double, std::milli>(now - last).count());
+        line += buf;
+        last = now;
+    }
+    void done(const char* call, std::size_t n, double kernel_ms) {
+        if (!on) return;
+        std::fprintf(stderr, "[nb200 trace] %s n=%zu:%s total=%.3fms kernels=%.3fms\n", call, n, line.c_str(),
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), kernel_ms);
+    }
+};
 
 [[noreturn]] void raise(const char* what, int rc, const nb200_ctx* ctx) {
     throw std::runtime_error(std::string("BruteForce_CUDA: ") + what + " failed (" + std::to_string(rc) +
@@ -80,12 +105,17 @@ std::vector<Vector<D>> brute_force_cuda_n_body(const std::vector<Body<D>>& bodie
     const std::size_t n = bodies.size();
     std::vector<Vector<D>> forces(n);          // zero-initialised like methods.cpp:9-15
     if (n == 0) return forces;
+    PhaseTrace tr;
     nb200_ctx* ctx = acquire(D, n);
+    tr.mark("context");
     int rc = nb200_upload_aos(ctx, bodies.data(), sizeof(Body<D>));
     if (rc != NB200_OK) raise("nb200_upload_aos", rc, ctx);
+    tr.mark("upload+pack");
     rc = nb200_forces(ctx, kG, kCutoffR2, reinterpret_cast<double*>(forces.data()));
     if (rc != NB200_OK) raise("nb200_forces", rc, ctx);
+    tr.mark("forces+download");
     nb200_last_elapsed_ms(ctx, &session().last_ms);
+    tr.done("brute_force_cuda_n_body", n, session().last_ms);
     return forces;
 }
 
