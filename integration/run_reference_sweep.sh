@@ -10,6 +10,7 @@ OUT="${1:-$ROOT/gpurun_out/sweep}"
 SRC="$ROOT/build/integration/sweep"
 [ -d "$SRC/nbody-sim-new" ] || { echo "$SRC is missing: run integration/build_patched_reference.py where /root/reference exists"; exit 1; }
 mkdir -p "$OUT"
+OUT="$(cd "$OUT" && pwd)"
 for PREC in 64 32; do
     WORK="$(mktemp -d)"
     cp -r "$SRC/." "$WORK/"

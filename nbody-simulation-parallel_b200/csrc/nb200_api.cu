@@ -333,6 +333,10 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
     CK(cudaMalloc(&s.vel, (size_t)D * tp * sizeof(double)));
     CK(cudaMalloc(&s.mass, tp * sizeof(double)));
     CK(cudaMalloc(&s.forces, std::max<size_t>(1, (size_t)s.n_local * D) * sizeof(double)));
+    // staging image of the AoS bodies, sized for the packed Body<D> record (40 / 56 bytes) so that no allocation is left
+    // for the first upload -- the reference times ONE call per process; a larger stride reallocates in nb200_upload_aos
+    s.aos_bytes = std::max<size_t>(1, ctx->n) * (size_t)(2 * D + 1) * sizeof(double);
+    CK(cudaMalloc(&s.aos_dev, s.aos_bytes));
     CK(cudaMalloc(&s.energy, 2 * sizeof(double)));
     CK(cudaMalloc(&s.bounds, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc(&s.tile_done, (tp / 32 + 1) * sizeof(unsigned)));

@@ -163,8 +163,17 @@ template <int D>
 void brute_force_cuda_warmup(std::size_t n) {
     std::lock_guard<std::mutex> lock(session_mutex());
     if (!n) return;
-    acquire(D, n);
+    nb200_ctx* ctx = acquire(D, n);
     touch_kernels(D, env_int("NB200_PRECISION", NB200_FP64));
+    // one throw-away upload of placeholder bodies through the same path and of the same size as the timed call's:
+    // the first pageable host-to-device copy of a process sets up the driver's staging buffers (measured in the
+    // reference's own sweep: 40-55 ms inside the first timed call of some runs, profiles/r02/sweep/phase_trace.txt)
+    std::vector<Body<D>> placeholder(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        for (int d = 0; d < D; ++d) placeholder[i].position[d] = 1.0 + (double)((i * 2654435761u + d * 40503u) % 9973);
+        placeholder[i].mass = 1.0;
+    }
+    nb200_upload_aos(ctx, placeholder.data(), sizeof(Body<D>));
 }
 
 double brute_force_cuda_last_kernel_ms() { return session().last_ms; }
