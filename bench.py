@@ -497,8 +497,10 @@ def run_product_arm(args) -> None:
         barrier()                           # every rank's rows are in the common array
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_val = interactions(n) * e2e_steps / e2e_s / 1e9
+    # N > 1: every rank copies only the rows it owns in both directions (shard-local upload, the default with the
+    # peer-store exchange); the per-step figure is the sum over the ranks = one pass over the n bodies each way
     h2d = n * (2 * DIM + 1) * 8
-    d2h = (hi - lo) * (2 * DIM + 1) * 8
+    d2h = n * (2 * DIM + 1) * 8
     release_host()
 
     # ---- parity gate on the context that was just timed (every rank takes part; the oracle runs on rank 0)
@@ -588,7 +590,8 @@ def run_product_arm(args) -> None:
         "wall_s_timed_region": round(wall, 3),
         "clocks": clocks,
         "e2e": {"value": round(e2e_val, 2), "unit": "G interactions/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "per_rank_bytes_each_way": (hi - lo) * (2 * DIM + 1) * 8},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }

@@ -183,7 +183,11 @@ struct Shard {
 
 constexpr int kMaxWorldP2P = NB_MAX_PEERS + 1;
 constexpr int kSymMaxSlots = kMaxWorldP2P / 2;      // senders of reaction sums per rank: floor(world / 2)
-constexpr size_t kFlagsBytes = 256;                 // 3 * kMaxWorldP2P flag words, padded
+// One allocation per shard (one IPC handle): 4 * kMaxWorldP2P flag words (step, upload epoch, reaction-sum pass, upload
+// ready; one per writer rank each), the per-rank bounds table of a shard-local upload (2 words per rank), then the
+// receive slots of the pair-symmetric pass.
+constexpr size_t kFlagsBytes = 512;
+constexpr int kBoundsTableWord = 4 * (NB_MAX_PEERS + 1);
 // The 256-target i-tile shape is opt-in only ("sym_itile" option): measured, it never beats the 1024
 // shape nor, below N ~ 32768, the ordered pass (N=16384: 1414 vs 1454 vs 1994 G inter/s).
 constexpr size_t kSymSmallN = 0;
@@ -218,9 +222,10 @@ struct nb200_ctx {
     unsigned long long epoch = 0;        // uploads so far (published on the epoch flags)
     std::vector<unsigned long long> acc_seq_issued;   // per driven shard: pair-symmetric passes with a reaction exchange so far
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
+    bool image_full = true;       // the staging image holds all n bodies (false: only the rows each shard owns)
     bool dead = false;            // a peer handshake timed out: the ranks' step counters may have diverged
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0, opt_seg_sub = 0;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0, opt_seg_sub = 0, opt_shard_upload = -1;
     long opt_spin_timeout_ms = 30000;   // bound of every device-side wait on a peer's flag
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
@@ -569,6 +574,30 @@ __global__ void nb_wait_flags_kernel(const unsigned long long* flags, int stride
         nb_wait_flag(flags + pr.r[p], want_step, timeout_ns, err_word, NB_WAIT_STEP, pr.r[p]) &&
             nb_wait_flag(flags + stride + pr.r[p], want_epoch, timeout_ns, err_word, NB_WAIT_EPOCH, pr.r[p]);
     }
+}
+
+// shard-local upload, step 1: this shard's bounds (max |x|, max |m| of its own rows) go into slot [rank] of every
+// shard's bounds table, then the "ready" flag tells the peers that (a) the bounds are there and (b) this shard has
+// finished every kernel of the previous upload epoch (stream order), so its source buffers may be overwritten
+__global__ void nb_publish_ready_kernel(NbForceParams P, const unsigned long long* my_bounds, int table_word, int ready_word,
+                                        unsigned long long epoch) {
+    if (threadIdx.x == 0) {
+        const unsigned long long bx = my_bounds[0], bm = my_bounds[1];
+        P.my_flags[table_word + 2 * P.my_rank] = bx;
+        P.my_flags[table_word + 2 * P.my_rank + 1] = bm;
+        for (int p = 0; p < P.n_peers; ++p) {
+            P.peer_flags[p][table_word + 2 * P.my_rank] = bx;
+            P.peer_flags[p][table_word + 2 * P.my_rank + 1] = bm;
+        }
+        __threadfence_system();
+        for (int p = 0; p < P.n_peers; ++p) nb_st_release_sys(P.peer_flags[p] + ready_word + P.my_rank, epoch);
+    }
+}
+// step 2: wait until every peer is ready for upload epoch `epoch`
+__global__ void nb_wait_ready_kernel(const unsigned long long* flags, int ready_word, int n_peers, PeerRanks pr,
+                                     unsigned long long epoch, unsigned long long timeout_ns, unsigned long long* err_word) {
+    const int p = threadIdx.x;
+    if (p < n_peers) nb_wait_flag(flags + ready_word + pr.r[p], epoch, timeout_ns, err_word, NB_WAIT_READY, pr.r[p]);
 }
 
 // publish this shard's epoch (upload count) on every peer's epoch flag
@@ -940,21 +969,39 @@ int init_common(nb200_ctx* ctx) {
 
 int publish_epoch(nb200_ctx* ctx);
 
-// AoS staging image -> tile-planar sources (both buffers) + FP64 master state, on every shard
+// AoS staging image -> tile-planar sources (both buffers) + FP64 master state, on every shard.  With a shard-local
+// image every shard packs the rows it owns and stores them into all shards' buffers (nb_pack_shard_kernel).
 int pack_sources(nb200_ctx* ctx) {
     const int D = ctx->dim;
     const size_t sd = ctx->aos_stride / sizeof(double);
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
         const int threads = 256;
-        const int blocks = (int)((ctx->nalloc + threads - 1) / threads);
+        if (ctx->image_full) {
+            const int blocks = (int)((ctx->nalloc + threads - 1) / threads);
 #define NB_PACK(DD, RR)                                                                              \
     nb_pack_kernel<DD, RR><<<blocks, threads, 0, s.compute>>>(                                       \
         s.aos_dev, sd, (long long)ctx->n, ctx->nalloc, (RR*)s.src[0], (RR*)s.src[1], ctx->pos_scale, \
         ctx->mass_scale, s.tgt_base, s.tpad, s.pos, s.vel, s.mass)
-        if (D == 3) { if (ctx->f64) NB_PACK(3, double); else NB_PACK(3, float); }
-        else        { if (ctx->f64) NB_PACK(2, double); else NB_PACK(2, float); }
+            if (D == 3) { if (ctx->f64) NB_PACK(3, double); else NB_PACK(3, float); }
+            else        { if (ctx->f64) NB_PACK(2, double); else NB_PACK(2, float); }
 #undef NB_PACK
+        } else {
+            NbPeerBufs pb;
+            memset(&pb, 0, sizeof pb);
+            pb.n_peers = s.n_peers;
+            for (int p = 0; p < s.n_peers; ++p) { pb.buf0[p] = s.peer_src[0][p]; pb.buf1[p] = s.peer_src[1][p]; }
+            const long long nbodies = ctx->ntiles * NB_TILE;
+            const int span = (int)(ctx->tiles_per_shard * NB_TILE);
+            const int blocks = (int)((s.tpad + (ctx->nalloc - nbodies) + threads - 1) / threads);
+#define NB_PACK(DD, RR)                                                                                              \
+    nb_pack_shard_kernel<DD, RR><<<blocks, threads, 0, s.compute>>>(                                                 \
+        s.aos_dev, sd, (long long)ctx->n, s.tgt_base, span, s.tpad, nbodies, ctx->nalloc, (RR*)s.src[0], (RR*)s.src[1], pb, \
+        ctx->pos_scale, ctx->mass_scale, s.pos, s.vel, s.mass)
+            if (D == 3) { if (ctx->f64) NB_PACK(3, double); else NB_PACK(3, float); }
+            else        { if (ctx->f64) NB_PACK(2, double); else NB_PACK(2, float); }
+#undef NB_PACK
+        }
         CK(cudaGetLastError());
         ctx->launches++;
     }
@@ -1051,11 +1098,76 @@ int publish_epoch(nb200_ctx* ctx) {
     return NB200_OK;
 }
 
+void set_fp32_scales(nb200_ctx* ctx, double xmax, double mmax) {
+    int ex = 0;
+    if (xmax > 0 && isfinite(xmax)) ctx->xmax = xmax;
+    if (!ctx->f64) {
+        if (xmax > 0 && isfinite(xmax)) { frexp(xmax, &ex); ctx->pos_scale = ldexp(1.0, -ex); }
+        if (mmax > 0 && isfinite(mmax)) { frexp(mmax, &ex); ctx->mass_scale = ldexp(1.0, -ex); }
+    }
+}
+
+// Shard-local upload: bounds of the own rows on every shard, exchanged through the peers' bounds tables together
+// with the "ready" handshake (no shard overwrites a peer's source buffers before that peer has finished with them);
+// every rank then derives the same power-of-two scales from the same table.
+int shard_local_bounds(nb200_ctx* ctx) {
+    const int D = ctx->dim;
+    const size_t sd = ctx->aos_stride / sizeof(double);
+    const unsigned long long next_epoch = ctx->epoch + 1;
+    const int ready_word = 3 * kMaxWorldP2P;
+    const unsigned long long timeout_ns = (unsigned long long)std::max(1L, ctx->opt_spin_timeout_ms) * 1000000ull;
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        CK(cudaMemsetAsync(s.bounds, 0, 2 * sizeof(unsigned long long), s.compute));
+        if (s.n_local > 0) {
+            const int blocks = (int)std::min<long long>(4LL * s.sms, (s.n_local + 255) / 256);
+            const double* rows = s.aos_dev + (size_t)s.tgt_base * sd;
+            if (D == 3) nb_bounds_kernel<3><<<blocks, 256, 0, s.compute>>>(rows, sd, s.n_local, s.bounds);
+            else nb_bounds_kernel<2><<<blocks, 256, 0, s.compute>>>(rows, sd, s.n_local, s.bounds);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
+        NbForceParams P;
+        memset(&P, 0, sizeof P);
+        P.n_peers = s.n_peers;
+        P.my_rank = s.rank;
+        P.my_flags = s.flags;
+        for (int p = 0; p < s.n_peers; ++p) P.peer_flags[p] = s.peer_flags[p];
+        nb_publish_ready_kernel<<<1, 32, 0, s.compute>>>(P, s.bounds, kBoundsTableWord, ready_word, next_epoch);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    double xmax = 0.0, mmax = 0.0;
+    for (Shard& s : ctx->shards) {
+        CK(cudaSetDevice(s.device));
+        nb_wait_ready_kernel<<<1, 32, 0, s.compute>>>(s.flags, ready_word, s.n_peers, PeerRanks(s), next_epoch, timeout_ns, s.err_dev);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        double table[2 * kMaxWorldP2P];
+        CK(cudaMemcpyAsync(table, s.flags + kBoundsTableWord, sizeof table, cudaMemcpyDeviceToHost, s.compute));
+        CK(cudaStreamSynchronize(s.compute));
+        if (s.err_host && *reinterpret_cast<volatile unsigned long long*>(s.err_host)) {
+            ctx->dead = true;
+            return fail(ctx, NB200_ESTATE, "rank %d: a peer did not enter upload %llu within %ld ms (uploads are collective "
+                        "across the ranks of an attached exchange); the context is unusable, destroy it on every rank",
+                        s.rank, next_epoch, ctx->opt_spin_timeout_ms);
+        }
+        for (int r = 0; r < ctx->world && r < kMaxWorldP2P; ++r) {
+            if (table[2 * r] > xmax) xmax = table[2 * r];
+            if (table[2 * r + 1] > mmax) mmax = table[2 * r + 1];
+        }
+    }
+    set_fp32_scales(ctx, xmax, mmax);
+    return NB200_OK;
+}
+
 // common tail of nb200_upload_aos / nb200_generate: the AoS image is in aos_dev on every shard
 int finish_upload(nb200_ctx* ctx) {
     const int D = ctx->dim;
     const size_t sd = ctx->aos_stride / sizeof(double);
-    if (ctx->n) {
+    if (!ctx->image_full) {
+        if (int rc = shard_local_bounds(ctx)) return rc;
+    } else if (ctx->n) {
         // bounds of the image, reduced on the device that already holds it (shard 0)
         Shard& s = ctx->shards[0];
         CK(cudaSetDevice(s.device));
@@ -1068,13 +1180,7 @@ int finish_upload(nb200_ctx* ctx) {
         double hb[2] = {0.0, 0.0};
         CK(cudaMemcpyAsync(hb, s.bounds, sizeof hb, cudaMemcpyDeviceToHost, s.compute));
         CK(cudaStreamSynchronize(s.compute));
-        const double xmax = hb[0], mmax = hb[1];
-        int ex = 0;
-        if (xmax > 0 && isfinite(xmax)) ctx->xmax = xmax;
-        if (!ctx->f64) {
-            if (xmax > 0 && isfinite(xmax)) { frexp(xmax, &ex); ctx->pos_scale = ldexp(1.0, -ex); }
-            if (mmax > 0 && isfinite(mmax)) { frexp(mmax, &ex); ctx->mass_scale = ldexp(1.0, -ex); }
-        }
+        set_fp32_scales(ctx, hb[0], hb[1]);
     }
     int rc = pack_sources(ctx);
     if (rc) return rc;
@@ -1300,6 +1406,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "variant")) ctx->opt_variant = (value >= 0 && value < kNumVariants) ? (int)value : -1;
     else if (!strcmp(key, "seg_tiles")) ctx->opt_seg_tiles = (int)std::max(0L, value);
     else if (!strcmp(key, "seg_sub")) ctx->opt_seg_sub = (int)std::max(0L, value);
+    else if (!strcmp(key, "shard_upload")) ctx->opt_shard_upload = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);
     else if (!strcmp(key, "overlap")) ctx->opt_overlap = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "trace")) ctx->opt_trace = value != 0;
@@ -1347,12 +1454,22 @@ int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
     // FP32 pair math runs on power-of-two-scaled sources (exact): |x'| <= 1, m' <= 1
     ctx->pos_scale = ctx->mass_scale = 1.0;
     ctx->xmax = 1.0;
+    // With the peer-store exchange attached every shard takes only the rows it owns from the caller's array and stores
+    // their source rows into all shards' buffers itself ("shard_upload" option, default on): 1/G of the PCIe traffic and of
+    // the packing per GPU.  The call is then collective over the ranks (bounded wait, NB200_ESTATE if a peer never comes).
+    ctx->image_full = !(ctx->world > 1 && !ctx->detached && ctx->p2p_ready && ctx->exchange == 1 && ctx->opt_shard_upload != 0);
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
         const size_t bytes = std::max<size_t>(1, ctx->n) * stride;
         if (s.aos_dev && s.aos_bytes < bytes) { CK(cudaFree(s.aos_dev)); s.aos_dev = nullptr; }
         if (!s.aos_dev) { CK(cudaMalloc(&s.aos_dev, bytes)); s.aos_bytes = bytes; }
-        if (ctx->n) CK(cudaMemcpyAsync(s.aos_dev, bodies, ctx->n * stride, cudaMemcpyHostToDevice, s.compute));
+        if (ctx->image_full) {
+            if (ctx->n) CK(cudaMemcpyAsync(s.aos_dev, bodies, ctx->n * stride, cudaMemcpyHostToDevice, s.compute));
+        } else if (s.n_local > 0) {
+            const size_t off = (size_t)s.tgt_base * stride;
+            CK(cudaMemcpyAsync(reinterpret_cast<char*>(s.aos_dev) + off, static_cast<const char*>(bodies) + off,
+                               (size_t)s.n_local * stride, cudaMemcpyHostToDevice, s.compute));
+        }
     }
     return finish_upload(ctx);
 }
@@ -1369,6 +1486,7 @@ int nb200_generate(nb200_ctx* ctx, int kind, unsigned long long seed, double G) 
     const size_t sd = stride / sizeof(double);
     ctx->pos_scale = ctx->mass_scale = 1.0;
     ctx->xmax = 1.0;
+    ctx->image_full = true;              // every shard generates (and packs) all n bodies: no PCIe, no exchange
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
         const size_t bytes = std::max<size_t>(1, ctx->n) * stride;

@@ -41,6 +41,59 @@ __global__ void nb_pack_kernel(const double* __restrict__ aos, size_t stride_d, 
     }
 }
 
+// Shard-local flavour (multi-GPU with the peer-store exchange): the image holds only the rows this shard owns; their
+// tile-planar source rows go to BOTH buffers of this shard and of every peer (plain stores on peer-mapped pointers over
+// NVLink), so no rank ever uploads or packs a body it does not own.  Thread t < tpad: own padded row t (rows past the
+// shard's tiles only reset the master state); t >= tpad: one of the slack rows behind the last tile (local only).
+struct NbPeerBufs {
+    void* buf0[NB_MAX_PEERS];
+    void* buf1[NB_MAX_PEERS];
+    int n_peers;
+};
+template <int D, typename real>
+__global__ void nb_pack_shard_kernel(const double* __restrict__ aos, size_t stride_d, long long n, long long tgt_base,
+                                     int span, int tpad, long long nbodies, long long nalloc,
+                                     real* __restrict__ src0, real* __restrict__ src1, NbPeerBufs peers,
+                                     double pos_scale, double mass_scale, double* __restrict__ pos,
+                                     double* __restrict__ vel, double* __restrict__ mass) {
+    constexpr int NP = D + 1;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool slack = t >= tpad;
+    const long long b = slack ? nbodies + (t - tpad) : tgt_base + t;
+    if (slack && b >= nalloc) return;
+    const bool own_row = !slack && t < span;
+    const bool real_body = own_row && b < n;
+    // padding rows sit on the shard's first body (or the origin of an empty shard) with mass 0: they add exactly 0
+    const bool have_anchor = tgt_base < n;
+    const double* rec = aos + (size_t)(real_body ? b : (have_anchor ? tgt_base : 0)) * stride_d;
+    double x[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = (real_body || have_anchor) ? rec[d] : 0.0;
+    const double m = real_body ? rec[2 * D] : 0.0;
+    if (own_row || slack) {
+        const size_t off = (size_t)(b / NB_TILE) * (NB_TILE * NP) + (b % NB_TILE);
+#pragma unroll
+        for (int d = 0; d <= D; ++d) {
+            const real v = d < D ? (real)(x[d] * pos_scale) : (real)(m * mass_scale);
+            src0[off + (size_t)d * NB_TILE] = v;
+            src1[off + (size_t)d * NB_TILE] = v;
+            if (own_row)
+                for (int p = 0; p < peers.n_peers; ++p) {
+                    static_cast<real*>(peers.buf0[p])[off + (size_t)d * NB_TILE] = v;
+                    static_cast<real*>(peers.buf1[p])[off + (size_t)d * NB_TILE] = v;
+                }
+        }
+    }
+    if (!slack) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            pos[(size_t)d * tpad + t] = own_row ? x[d] : 0.0;
+            vel[(size_t)d * tpad + t] = real_body ? rec[D + d] : 0.0;
+        }
+        mass[t] = m;
+    }
+}
+
 // max |coordinate| and max |mass| over the AoS image (FP32 mode picks its power-of-two source
 // scales from them).  Non-negative doubles order like their bit patterns, so the reduction ends
 // in one 64-bit atomicMax per warp.  NaNs are ignored (every comparison with them is false).

@@ -68,6 +68,7 @@ struct NbForceParams {
 #define NB_WAIT_STEP 1ull
 #define NB_WAIT_EPOCH 2ull
 #define NB_WAIT_REACTION 3ull
+#define NB_WAIT_READY 4ull
 
 // ------------------------------------------------------------------ mbarrier / TMA (sm_90+ PTX)
 __device__ __forceinline__ uint32_t nb_smem_u32(const void* p) {

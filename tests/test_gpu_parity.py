@@ -463,6 +463,23 @@ def test_single_process_multi_gpu_matches_one_gpu(pkg, ngpus, prec):
                                            options={"detect": 1, "symmetric": 1, "sym_ti": ti, "seg_tiles": 3})
         err = np.abs(ag - a1).max() / np.abs(a1).max()
         assert err <= tol, f"cross-rank symmetric TI={ti}: {err:.3e}"
+    # shard-local upload (default: every shard takes only its own rows from the caller's array and stores their source
+    # rows into all shards' buffers) against the full upload on every shard: identical state, identical trajectories
+    for b_up in (b, pkg.generators.reference_range(n, 3, seed=3)):
+        runs = {}
+        for shard_upload in (1, 0):
+            with pkg.NBodyCuda(3, n, prec, ngpus) as ctx:
+                ctx.set_option("shard_upload", shard_upload)
+                ctx.upload(b_up)
+                f = ctx.forces()
+                ctx.step(1e-3, 3)
+                ctx.upload(b_up)                     # a second epoch over buffers the peers have read
+                ctx.step(1e-3, 2)
+                out = b_up.copy()
+                ctx.download(out)
+            runs[shard_upload] = (f, out)
+        assert rel(pkg, runs[1][0], runs[0][0]).max() <= (1e-13 if prec == 64 else 1e-6)
+        assert np.abs(runs[1][1] - runs[0][1]).max() <= (1e-12 if prec == 64 else 1e-6) * np.abs(runs[0][1]).max()
     # ragged shards: the last i-tile of every shard reaches into the next shard's bodies
     br = pkg.generators.plummer(25000 + 1000 * ngpus, seed=6)     # 53 / 29 / 17 tiles per shard
     r1 = pkg.brute_force_cuda_simulate(br, 1e-3, 6, prec, options={"detect": 1, "symmetric": 0})
