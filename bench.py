@@ -321,7 +321,10 @@ def parity_gate(pkg, oracle, D, ctx, bodies, dim, prec, dt, rank, world, local, 
             tol_x = 1e-12 if prec == 64 else 1e-6
             out["vs_1gpu"] = {"bodies": n, "state_max_diff_rel": dx, "forces_max_rel_diff": float(df.max()),
                               "forces_p99_rel_diff": float(np.percentile(df, 99)), "tol_state": tol_x}
-            ok = ok and dx <= tol_x and (df.max() <= 1e-12 if prec == 64 else np.percentile(df, 99) <= 1e-5)
+            # forces: N GPUs evaluate the ordered pass per shard, one GPU the pair-symmetric pass -- two summation orders,
+            # each within 1e-12 of the reference (checked above), hence within 2e-12 of each other
+            ok = ok and dx <= tol_x and (df.max() <= 2e-12 if prec == 64 else np.percentile(df, 99) <= 1e-5)
+            out["vs_1gpu"]["tol_forces"] = "max <= 2e-12" if prec == 64 else "p99 <= 1e-5"
         out["ok"] = bool(ok)
     ok_all = bcast_ok(out["ok"] if out else True)
     return out, ok_all
