@@ -179,6 +179,30 @@ int nb200_compare_forces(nb200_ctx* a, nb200_ctx* b, double* stats_out);
  * written (rank contexts: the ones they own), 0 when n < 3, or a negative NB200_E* code. */
 int nb200_validation_forces(nb200_ctx* ctx, double* forces_out, long long* index_out, int cap);
 
+/* ---- next row of the suite: the P2P (leaf) step of its tree codes --------------------------------- */
+
+/* Direct sums over LEAF LISTS, the particle-to-particle step of the reference's Barnes-Hut / BVH / FMM methods:
+ *   BVH<D>::calculate_force, leaf branch            bvh.cpp:149-177   (eps_same = 1e-9, cutoff_r2 = 1e-9)
+ *   FMM<D>::calculate_accurate_force, leaf branch   fmm.cpp:622-637   (skip_same_index = 1, cutoff_r2 = 1e-10)
+ *   fmm_parlay.cpp:918-1023                                           (same law and guards)
+ * The pair law is the brute-force methods' (|F| = G m_i m_j / r^3 along d = p_j - p_i), the sign the tree codes'
+ * (sign = +1: force += diff.normalized() * mag, attractive; -1 gives the brute-force convention).
+ *   bodies        n records of Body<D> (body.h:7-19), `stride` bytes apart
+ *   leaf_offsets  [n_leaves + 1] into leaf_bodies; leaf_bodies = body indices, leaf after leaf (a body sits in at most
+ *                 one leaf)
+ *   nbr_offsets   [n_leaves + 1] into nbr_leaves; nbr_leaves = the SOURCE leaves of each target leaf (the leaf itself
+ *                 included when its own bodies interact, as in the reference's leaf loop)
+ *   eps_same      >= 0: a pair is skipped when every |d_k| <= eps_same (bvh.cpp:156-163); < 0: test off
+ *   cutoff_r2     pairs with r^2 < cutoff_r2 are skipped
+ *   skip_same_index  1: a body never interacts with itself even at cutoff_r2 = 0 (fmm.cpp:624)
+ *   forces_out    n * dim doubles, Vector<D> layout, body order; bodies in no leaf get zero
+ *   kernel_ms     optional: device time of the gather + P2P kernels (CUDA events)
+ * FP64 throughout (<= 1e-12 against the reference's own leaf loop).  Context-free: errors via nb200_last_error(NULL). */
+int nb200_p2p_leaves(int device, int dim, size_t n, const void* bodies, size_t stride, size_t n_leaves,
+                     const long long* leaf_offsets, const long long* leaf_bodies, const long long* nbr_offsets,
+                     const long long* nbr_leaves, double G, double cutoff_r2, double eps_same, int skip_same_index,
+                     int sign, double* forces_out, double* kernel_ms);
+
 /* ---- introspection / measurement --------------------------------------------------------- */
 
 /* Device time (CUDA events on the launching stream, max over this context's devices) of the

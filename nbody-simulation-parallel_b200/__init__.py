@@ -216,6 +216,37 @@ def measure_fp32_peak(device: int = 0) -> float:
     return t.value
 
 
+#: the guards of the reference's tree codes for their leaf (P2P) sums
+P2P_BVH = {"eps_same": 1e-9, "cutoff": 1e-9, "skip_same_index": 0}       # bvh.cpp:156-169
+P2P_FMM = {"eps_same": -1.0, "cutoff": 1e-10, "skip_same_index": 1}      # fmm.cpp:624-628
+
+
+def p2p_leaves_cuda(bodies: np.ndarray, leaf_offsets, leaf_bodies, nbr_offsets, nbr_leaves, G: float = G_REF,
+                    cutoff: float = 1e-9, eps_same: float = 1e-9, skip_same_index: int = 0, sign: int = 1,
+                    device: int = 0, return_ms: bool = False):
+    """The leaf (P2P) step of the suite's tree codes on the device (nb200_p2p_leaves): every body of target leaf l
+    receives the direct sum over the bodies of the leaves ``nbr_leaves[nbr_offsets[l]:nbr_offsets[l+1]]``, with the
+    tree codes' attractive sign and guards (defaults: BVH<D>::calculate_force, bvh.cpp:149-177)."""
+    b = np.ascontiguousarray(bodies, dtype=np.float64)
+    dim = _dim_of(b)
+    lo = np.ascontiguousarray(leaf_offsets, dtype=np.int64)
+    lb = np.ascontiguousarray(leaf_bodies, dtype=np.int64)
+    no = np.ascontiguousarray(nbr_offsets, dtype=np.int64)
+    nl = np.ascontiguousarray(nbr_leaves, dtype=np.int64)
+    out = np.zeros((b.shape[0], dim))
+    ms = ctypes.c_double()
+    ll = ctypes.POINTER(ctypes.c_longlong)
+    lib = _lib.load()
+    rc = lib.nb200_p2p_leaves(device, dim, b.shape[0], b.ctypes.data, b.strides[0] if b.shape[0] else 8 * (2 * dim + 1),
+                              max(lo.shape[0] - 1, 0), lo.ctypes.data_as(ll), lb.ctypes.data_as(ll), no.ctypes.data_as(ll),
+                              nl.ctypes.data_as(ll), G, cutoff, eps_same, int(skip_same_index), int(sign),
+                              out.ctypes.data_as(_lib._dp), ctypes.byref(ms))
+    if rc != 0:
+        msg = lib.nb200_last_error(None)
+        raise NB200Error(f"nb200_p2p_leaves failed ({rc}): {msg.decode() if msg else ''}")
+    return (out, ms.value) if return_ms else out
+
+
 def brute_force_cuda_n_body(bodies: np.ndarray, precision: int = NB200_FP64, ngpus: int = 1, G: float = G_REF,
                             cutoff: float = CUTOFF_REF, options: dict | None = None) -> np.ndarray:
     """Forces on every body, (n, D) float64 in body order -- the ``BruteForce_CUDA`` method beside
@@ -248,4 +279,5 @@ def brute_force_cuda_simulate(bodies: np.ndarray, dt: float, steps: int, precisi
 
 __all__ = ["NBodyCuda", "NB200Error", "NB200_FP32", "NB200_FP64", "G_REF", "CUTOFF_REF", "FP32_TOL", "FP32_PER_KAPPA",
            "fp32_error_bound",
-           "measure_fp32_peak", "brute_force_cuda_n_body", "brute_force_cuda_simulate", "generators"]
+           "measure_fp32_peak", "brute_force_cuda_n_body", "brute_force_cuda_simulate", "p2p_leaves_cuda", "P2P_BVH", "P2P_FMM",
+           "generators"]

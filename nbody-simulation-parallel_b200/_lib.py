@@ -43,6 +43,10 @@ SIGNATURES = {
     "nb200_energy": (_c.c_int, [_ctx_p, _c.c_double, _c.c_double, _dp, _dp]),
     "nb200_accuracy_pct": (_c.c_int, [_ctx_p, _dp, _dp, _dp]),
     "nb200_compare_forces": (_c.c_int, [_ctx_p, _ctx_p, _dp]),
+    "nb200_p2p_leaves": (_c.c_int, [_c.c_int, _c.c_int, _c.c_size_t, _c.c_void_p, _c.c_size_t, _c.c_size_t,
+                                    _c.POINTER(_c.c_longlong), _c.POINTER(_c.c_longlong), _c.POINTER(_c.c_longlong),
+                                    _c.POINTER(_c.c_longlong), _c.c_double, _c.c_double, _c.c_double, _c.c_int, _c.c_int,
+                                    _dp, _dp]),
     "nb200_validation_forces": (_c.c_int, [_ctx_p, _dp, _c.POINTER(_c.c_longlong), _c.c_int]),
     "nb200_measure_fp32_peak": (_c.c_int, [_c.c_int, _dp]),
     "nb200_debug_sym_exchange": (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_c.c_int), _c.c_int]),

@@ -34,6 +34,7 @@
 #include "nb_aux.cuh"
 #include "nb_force.cuh"
 #include "nb_force_sym.cuh"
+#include "nb_p2p.cuh"
 
 #define NB200_VERSION_STR "nb200 0.1 (sm_100a)"
 
@@ -1905,6 +1906,112 @@ int nb200_compare_forces(nb200_ctx* ctx, nb200_ctx* other, double* stats_out) {
         stats_out[3] += (double)h[2 + NB_CMP_BINS - 1];
         for (int k = 0; k < NB_CMP_BINS - 1; ++k) stats_out[4 + k] += (double)h[2 + k];
     }
+    return NB200_OK;
+}
+
+int nb200_p2p_leaves(int device, int dim, size_t n, const void* bodies, size_t stride, size_t n_leaves,
+                     const long long* leaf_offsets, const long long* leaf_bodies, const long long* nbr_offsets,
+                     const long long* nbr_leaves, double G, double cutoff_r2, double eps_same, int skip_same_index, int sign,
+                     double* forces_out, double* kernel_ms) {
+    nb200_ctx* ctx = nullptr;              // errors of this context-free call go to nb200_last_error(NULL)
+    if (dim != 2 && dim != 3) return fail(nullptr, NB200_EINVAL, "dim must be 2 or 3, got %d", dim);
+    if (sign != 1 && sign != -1) return fail(nullptr, NB200_EINVAL, "sign must be +1 (attractive, tree codes) or -1 (brute-force convention)");
+    if (!(cutoff_r2 >= 0.0)) return fail(nullptr, NB200_EINVAL, "cutoff_r2 must be >= 0");
+    if (n && (!bodies || !forces_out)) return fail(nullptr, NB200_EINVAL, "null bodies / forces_out");
+    if (stride < (size_t)(2 * dim + 1) * sizeof(double) || stride % sizeof(double)) return fail(nullptr, NB200_EINVAL, "bad stride %zu", stride);
+    if (n_leaves && (!leaf_offsets || !nbr_offsets)) return fail(nullptr, NB200_EINVAL, "null leaf / neighbour offsets");
+    // the lists come from the caller's tree: check them before anything is indexed with them on the device
+    const long long total = n_leaves ? leaf_offsets[n_leaves] : 0, n_nbr = n_leaves ? nbr_offsets[n_leaves] : 0;
+    if (n_leaves && (leaf_offsets[0] != 0 || nbr_offsets[0] != 0 || total < 0 || n_nbr < 0))
+        return fail(nullptr, NB200_EINVAL, "offset arrays must start at 0 and be non-negative");
+    for (size_t l = 0; l < n_leaves; ++l)
+        if (leaf_offsets[l + 1] < leaf_offsets[l] || nbr_offsets[l + 1] < nbr_offsets[l])
+            return fail(nullptr, NB200_EINVAL, "offsets of leaf %zu decrease", l);
+    if ((total && !leaf_bodies) || (n_nbr && !nbr_leaves)) return fail(nullptr, NB200_EINVAL, "null leaf_bodies / nbr_leaves");
+    {
+        std::vector<unsigned char> seen(n, 0);
+        for (long long k = 0; k < total; ++k) {
+            if (leaf_bodies[k] < 0 || (size_t)leaf_bodies[k] >= n) return fail(nullptr, NB200_EINVAL, "leaf_bodies[%lld] = %lld is not a body", k, leaf_bodies[k]);
+            if (seen[leaf_bodies[k]]++) return fail(nullptr, NB200_EINVAL, "body %lld sits in two leaves", leaf_bodies[k]);
+        }
+    }
+    for (long long q = 0; q < n_nbr; ++q)
+        if (nbr_leaves[q] < 0 || (size_t)nbr_leaves[q] >= n_leaves) return fail(nullptr, NB200_EINVAL, "nbr_leaves[%lld] = %lld is not a leaf", q, nbr_leaves[q]);
+    int have = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&have);
+    if (e0 != cudaSuccess || have == 0)
+        return fail(nullptr, NB200_ECUDA, "no CUDA device: %s (libnb200 has no CPU fallback)", e0 == cudaSuccess ? "device count is 0" : cudaGetErrorString(e0));
+    if (device < 0 || device >= have) return fail(nullptr, NB200_EINVAL, "device %d not visible (%d devices)", device, have);
+    for (size_t i = 0; i < n * (size_t)dim; ++i) forces_out[i] = 0.0;         // bodies in no leaf: zero, like Vector<D>()
+    if (kernel_ms) *kernel_ms = 0.0;
+    if (!n || !total) return NB200_OK;
+    CK(cudaSetDevice(device));
+    const size_t sd = stride / sizeof(double);
+    double *d_aos = nullptr, *d_pos = nullptr, *d_mass = nullptr, *d_forces = nullptr;
+    long long *d_lbody = nullptr, *d_loff = nullptr, *d_noff = nullptr, *d_nleaf = nullptr;
+    cudaEvent_t e_start = nullptr, e_stop = nullptr;
+    cudaStream_t st = nullptr;
+    int rc = NB200_OK;
+    auto release = [&]() {
+        cudaFree(d_aos); cudaFree(d_pos); cudaFree(d_mass); cudaFree(d_forces);
+        cudaFree(d_lbody); cudaFree(d_loff); cudaFree(d_noff); cudaFree(d_nleaf);
+        if (e_start) cudaEventDestroy(e_start);
+        if (e_stop) cudaEventDestroy(e_stop);
+        if (st) cudaStreamDestroy(st);
+    };
+#define P2P_CK(call)                                                                                                   \
+    do {                                                                                                               \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess) {                                                                                       \
+            rc = fail(nullptr, NB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            release();                                                                                                 \
+            return rc;                                                                                                 \
+        }                                                                                                              \
+    } while (0)
+    P2P_CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    P2P_CK(cudaEventCreate(&e_start));
+    P2P_CK(cudaEventCreate(&e_stop));
+    P2P_CK(cudaMalloc(&d_aos, n * stride));
+    P2P_CK(cudaMalloc(&d_pos, (size_t)dim * total * sizeof(double)));
+    P2P_CK(cudaMalloc(&d_mass, (size_t)total * sizeof(double)));
+    P2P_CK(cudaMalloc(&d_forces, n * (size_t)dim * sizeof(double)));
+    P2P_CK(cudaMalloc(&d_lbody, (size_t)total * sizeof(long long)));
+    P2P_CK(cudaMalloc(&d_loff, (n_leaves + 1) * sizeof(long long)));
+    P2P_CK(cudaMalloc(&d_noff, (n_leaves + 1) * sizeof(long long)));
+    P2P_CK(cudaMalloc(&d_nleaf, std::max<size_t>(1, (size_t)n_nbr) * sizeof(long long)));
+    P2P_CK(cudaMemcpyAsync(d_aos, bodies, n * stride, cudaMemcpyHostToDevice, st));
+    P2P_CK(cudaMemcpyAsync(d_lbody, leaf_bodies, (size_t)total * sizeof(long long), cudaMemcpyHostToDevice, st));
+    P2P_CK(cudaMemcpyAsync(d_loff, leaf_offsets, (n_leaves + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    P2P_CK(cudaMemcpyAsync(d_noff, nbr_offsets, (n_leaves + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (n_nbr) P2P_CK(cudaMemcpyAsync(d_nleaf, nbr_leaves, (size_t)n_nbr * sizeof(long long), cudaMemcpyHostToDevice, st));
+    P2P_CK(cudaMemsetAsync(d_forces, 0, n * (size_t)dim * sizeof(double), st));
+    NbP2PParams Q;
+    memset(&Q, 0, sizeof Q);
+    Q.lpos = d_pos; Q.lmass = d_mass; Q.lbody = d_lbody; Q.leaf_off = d_loff; Q.nbr_off = d_noff; Q.nbr_leaf = d_nleaf;
+    Q.forces = d_forces; Q.total = total; Q.n_leaves = (long long)n_leaves;
+    Q.G = G; Q.cutoff = cutoff_r2; Q.eps_same = eps_same; Q.skip_same_index = skip_same_index; Q.sign = (double)sign;
+    cudaDeviceProp prop;
+    P2P_CK(cudaGetDeviceProperties(&prop, device));
+    const int gb = (int)((total + 255) / 256);
+    const int grid = (int)std::min<long long>((long long)n_leaves, 16LL * prop.multiProcessorCount);
+    P2P_CK(cudaEventRecord(e_start, st));
+    if (dim == 3) {
+        nb_p2p_gather_kernel<3><<<gb, 256, 0, st>>>(d_aos, sd, d_lbody, total, d_pos, d_mass);
+        nb_p2p_leaf_kernel<3><<<grid, NB_P2P_BLOCK, 0, st>>>(Q);
+    } else {
+        nb_p2p_gather_kernel<2><<<gb, 256, 0, st>>>(d_aos, sd, d_lbody, total, d_pos, d_mass);
+        nb_p2p_leaf_kernel<2><<<grid, NB_P2P_BLOCK, 0, st>>>(Q);
+    }
+    P2P_CK(cudaGetLastError());
+    P2P_CK(cudaEventRecord(e_stop, st));
+    P2P_CK(cudaMemcpyAsync(forces_out, d_forces, n * (size_t)dim * sizeof(double), cudaMemcpyDeviceToHost, st));
+    P2P_CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    P2P_CK(cudaEventElapsedTime(&ms, e_start, e_stop));
+    if (kernel_ms) *kernel_ms = ms;
+#undef P2P_CK
+    release();
+    (void)ctx;
     return NB200_OK;
 }
 

@@ -75,6 +75,8 @@ class _Oracle:
         L.oracle_energy.argtypes = [ctypes.c_int, sz, _dp, ctypes.c_double, ctypes.c_double, _dp, _dp]
         L.oracle_condition.argtypes = [ctypes.c_int, sz, _dp, ctypes.c_double, ctypes.c_double, _dp]
         L.oracle_condition_targets.argtypes = [ctypes.c_int, sz, _dp, ctypes.c_double, ctypes.c_double, _ip, sz, _dp]
+        L.oracle_p2p_leaves.argtypes = [ctypes.c_int, sz, _dp, sz, _ip, _ip, _ip, _ip, ctypes.c_double, ctypes.c_double,
+                                        ctypes.c_double, ctypes.c_int, ctypes.c_int, _dp]
         L.oracle_accuracy_pct.argtypes = [ctypes.c_int, sz, _dp, _dp]
         L.oracle_accuracy_pct.restype = ctypes.c_double
         L.oracle_num_threads.restype = ctypes.c_int
@@ -166,6 +168,25 @@ def condition_targets(bodies, targets, G=G_REF, cutoff=CUTOFF_REF):
     return out
 
 
+def p2p_leaves(bodies, leaf_offsets, leaf_bodies, nbr_offsets, nbr_leaves, G=G_REF, cutoff=1e-9, eps_same=1e-9,
+               skip_same_index=0, sign=1):
+    """The leaf (P2P) branch of the reference's tree codes, restated (bvh.cpp:149-177; fmm.cpp:622-637 with
+    eps_same=-1, cutoff=1e-10, skip_same_index=1): direct sums over leaf lists."""
+    dim = _dim_of(bodies)
+    b = _as_bodies(bodies, dim)
+    lo = np.ascontiguousarray(leaf_offsets, dtype=np.int64)
+    lb = np.ascontiguousarray(leaf_bodies, dtype=np.int64)
+    no = np.ascontiguousarray(nbr_offsets, dtype=np.int64)
+    nl = np.ascontiguousarray(nbr_leaves, dtype=np.int64)
+    out = np.zeros((b.shape[0], dim))
+    rc = _o().oracle_p2p_leaves(dim, b.shape[0], _p(b), lo.shape[0] - 1, lo.ctypes.data_as(_ip), lb.ctypes.data_as(_ip),
+                                no.ctypes.data_as(_ip), nl.ctypes.data_as(_ip), G, cutoff, eps_same, int(skip_same_index),
+                                int(sign), _p(out))
+    if rc:
+        raise RuntimeError(f"oracle p2p_leaves rc={rc}")
+    return out
+
+
 def accuracy_pct(forces_, reference):
     """utils.h:170-219 (the reference's -a 1 column)."""
     f = np.ascontiguousarray(forces_, dtype=np.float64)
@@ -189,6 +210,10 @@ class _Ref:
         L.ref_simulate.restype = ctypes.c_int
         L.ref_accuracy_pct.argtypes = [ctypes.c_int, sz, _dp, _dp]
         L.ref_accuracy_pct.restype = ctypes.c_double
+        L.ref_bvh_single_leaf_forces.argtypes = [ctypes.c_int, sz, ctypes.c_void_p, _dp]
+        L.ref_bvh_single_leaf_forces.restype = ctypes.c_int
+        L.ref_bvh_forces.argtypes = [ctypes.c_int, sz, ctypes.c_void_p, _dp]
+        L.ref_bvh_forces.restype = ctypes.c_double
         L.ref_G.restype = ctypes.c_double
         L.ref_omp_threads.restype = ctypes.c_int
         L.ref_parlay_workers.restype = ctypes.c_int
@@ -230,6 +255,29 @@ def ref_simulate(bodies, dt, nsteps, variant="omp_2"):
     if rc:
         raise RuntimeError(f"reference simulate rc={rc}")
     return b
+
+
+def ref_bvh_single_leaf_forces(bodies):
+    """The reference's own compiled BVH<D>::calculate_force on a tree whose root is one leaf holding every body
+    (max_bodies_per_leaf >= n): its leaf loop (bvh.cpp:149-177) as a direct sum over all bodies."""
+    dim = _dim_of(bodies)
+    b = _as_bodies(bodies, dim)
+    out = np.zeros((b.shape[0], dim))
+    rc = _r().ref_bvh_single_leaf_forces(dim, b.shape[0], b.ctypes.data, _p(out))
+    if rc:
+        raise RuntimeError(f"reference BVH leaf forces rc={rc}")
+    return out
+
+
+def ref_bvh_forces(bodies, want_forces=True):
+    """The reference's bvh_seq_n_body<D> end to end (leaf size 16): (forces or None, seconds)."""
+    dim = _dim_of(bodies)
+    b = _as_bodies(bodies, dim)
+    out = np.zeros((b.shape[0], dim)) if want_forces else None
+    secs = _r().ref_bvh_forces(dim, b.shape[0], b.ctypes.data, _p(out) if want_forces else None)
+    if secs < 0:
+        raise RuntimeError(f"reference BVH failed ({secs})")
+    return out, secs
 
 
 def ref_accuracy_pct(forces_, reference):

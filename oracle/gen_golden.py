@@ -80,5 +80,40 @@ def main():
               f"|F|max={np.abs(f_omp2).max():.3e}")
 
 
+def p2p_cases():
+    """Inputs for the leaf (P2P) step of the tree codes: the reference's ranges and the unit cube, each with an exact
+    duplicate (the per-component same-position test, bvh.cpp:156-163), a pair under the 1e-9 guard on r^2
+    (bvh.cpp:170) and a pair just above it."""
+    out = {}
+    for name, b in (("p2p_bvh3d_refrange_n300", gen.reference_range(300, 3, seed=61)),
+                    ("p2p_bvh2d_refrange_n300", gen.reference_range(300, 2, seed=62)),
+                    ("p2p_bvh3d_cube_n500", gen.uniform_cube(500, 3, seed=63)),
+                    ("p2p_bvh2d_cube_n77", gen.uniform_cube(77, 2, seed=64))):
+        dim = (b.shape[1] - 1) // 2
+        b[5, :dim] = b[4, :dim]                       # same position: skipped
+        b[9, 0] = b[8, 0] + 2.0e-5                    # r^2 = 4e-10 < 1e-9 ...
+        b[9, 1:dim] = b[8, 1:dim]                     # ... skipped
+        b[13, 0] = b[12, 0] + 4.0e-5                  # r^2 = 1.6e-9: kept (dominates both bodies)
+        b[13, 1:dim] = b[12, 1:dim]
+        out[name] = b
+    return out
+
+
+def p2p_main():
+    """tests/golden/p2p/*.npz: BVH<D>::calculate_force of the compiled reference on a tree whose root is a single leaf
+    (max_bodies_per_leaf >= n): its leaf loop (bvh.cpp:149-177) as the direct sum over all bodies."""
+    out_dir = os.path.join(OUT, "p2p")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, bodies in p2p_cases().items():
+        f = oracle.ref_bvh_single_leaf_forces(bodies)
+        np.savez(os.path.join(out_dir, name + ".npz"), bodies=bodies, forces_bvh_leaf=f,
+                 G=np.float64(oracle.ref_threads()["G"]), cutoff=np.float64(1e-9), eps_same=np.float64(1e-9))
+        print(f"{name}: n={bodies.shape[0]} |F|max={np.abs(f).max():.3e}")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "p2p":
+        p2p_main()          # the brute-force fixtures stay as committed
+    else:
+        main()
+        p2p_main()

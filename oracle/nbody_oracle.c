@@ -318,6 +318,59 @@ int oracle_condition_targets(int D, size_t n, const double *bodies, double G, do
     return 0;
 }
 
+/*
+ * The leaf (P2P) branch of the tree codes, restated literally:
+ *   BVH<D>::calculate_force, node->is_leaf       bvh.cpp:149-177   eps_same = 1e-9, cutoff = 1e-9, skip_same_index = 0
+ *   FMM<D>::calculate_accurate_force, leaf       fmm.cpp:622-637   eps_same < 0,    cutoff = 1e-10, skip_same_index = 1
+ * For every body i of target leaf l and every body j of the leaves nbr_leaves[nbr_off[l] .. nbr_off[l+1]), in list order:
+ *   same_position = all_d |p_i[d] - p_j[d]| <= eps_same  -> skip      bvh.cpp:156-163
+ *   diff = p_j - p_i; dist_sq = sum diff^2 (from 0.0, d ascending)    bvh.cpp:166-167, vector.h:81-85
+ *   if (dist_sq < cutoff) skip                                         bvh.cpp:170
+ *   dist = sqrt(dist_sq); force_mag = G * m_i * m_j / (dist_sq * dist) bvh.cpp:172-173
+ *   force += diff.normalized() * force_mag                             bvh.cpp:175  (attractive; sign = -1 flips it)
+ * forces of bodies that sit in no leaf stay zero.
+ */
+int oracle_p2p_leaves(int D, size_t n, const double *bodies, size_t n_leaves, const long long *leaf_off,
+                      const long long *leaf_bodies, const long long *nbr_off, const long long *nbr_leaves, double G,
+                      double cutoff, double eps_same, int skip_same_index, int sign, double *forces)
+{
+    if (D != 2 && D != 3) return -1;
+    for (size_t k = 0; k < n * (size_t)D; k++) forces[k] = 0.0;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (size_t l = 0; l < n_leaves; l++) {
+        for (long long a = leaf_off[l]; a < leaf_off[l + 1]; a++) {
+            const long long i = leaf_bodies[a];
+            const double *pi = POS(bodies, i, D);
+            double f[3] = {0.0, 0.0, 0.0};
+            for (long long q = nbr_off[l]; q < nbr_off[l + 1]; q++) {
+                const long long sl = nbr_leaves[q];
+                for (long long b = leaf_off[sl]; b < leaf_off[sl + 1]; b++) {
+                    const long long j = leaf_bodies[b];
+                    const double *pj = POS(bodies, j, D);
+                    if (skip_same_index && j == i) continue;
+                    if (eps_same >= 0.0) {
+                        int same = 1;
+                        for (int d = 0; d < D; d++)
+                            if (fabs(pi[d] - pj[d]) > eps_same) { same = 0; break; }
+                        if (same) continue;
+                    }
+                    double diff[3], dist_sq = 0.0;
+                    for (int d = 0; d < D; d++) diff[d] = pj[d] - pi[d];
+                    for (int d = 0; d < D; d++) dist_sq += diff[d] * diff[d];
+                    if (dist_sq < cutoff) continue;
+                    const double dist = sqrt(dist_sq);
+                    const double force_mag = G * MASS(bodies, i, D) * MASS(bodies, j, D) / (dist_sq * dist);
+                    const double mag = sqrt(dist_sq);
+                    if (mag < 1e-10) continue;                    /* normalized() -> zero vector: adds 0 (vector.h:95) */
+                    for (int d = 0; d < D; d++) f[d] += (diff[d] / mag) * force_mag;
+                }
+            }
+            for (int d = 0; d < D; d++) forces[(size_t)i * D + d] = sign < 0 ? -f[d] : f[d];
+        }
+    }
+    return 0;
+}
+
 /* compute_accuracy_omp, utils.h:170-219: % of bodies whose every component is within
  * 1 % of the reference force (|ref| < 1e-20 -> absolute test |f| <= 1e-9). */
 double oracle_accuracy_pct(int D, size_t n, const double *forces, const double *ref)

@@ -159,6 +159,48 @@ double ref_accuracy_pct(int dim, size_t n, const double* forces, const double* r
     return compute_accuracy_omp<3>(a, b);
 }
 
+// The reference's own leaf (P2P) loop: BVH<D>::calculate_force on a tree whose root IS a leaf (max_bodies >= n), i.e.
+// the direct sum of bvh.cpp:149-177 over all bodies, in body order, with the reference's guards.  forces_out = n * dim.
+int ref_bvh_single_leaf_forces(int dim, size_t n, const void* bodies_aos, double* forces_out) {
+    try {
+        if (dim == 2) {
+            std::vector<Body<2>> b = to_vec<2>(bodies_aos, n);
+            BVH<2> tree(b, (int)n + 1);
+            store<2>(tree.calculate_forces(b), forces_out);
+        } else if (dim == 3) {
+            std::vector<Body<3>> b = to_vec<3>(bodies_aos, n);
+            BVH<3> tree(b, (int)n + 1);
+            store<3>(tree.calculate_forces(b), forces_out);
+        } else return -1;
+        return 0;
+    } catch (...) {
+        return -2;
+    }
+}
+
+// The reference's BVH method end to end (default leaf size 16, opening criterion and all): for timing beside the leaf step.
+double ref_bvh_forces(int dim, size_t n, const void* bodies_aos, double* forces_out) {
+    using clk = std::chrono::high_resolution_clock;
+    try {
+        if (dim == 2) {
+            std::vector<Body<2>> b = to_vec<2>(bodies_aos, n);
+            auto t0 = clk::now();
+            std::vector<Vector<2>> f = bvh_seq_n_body<2>(b);
+            auto t1 = clk::now();
+            if (forces_out) store<2>(f, forces_out);
+            return std::chrono::duration<double>(t1 - t0).count();
+        }
+        std::vector<Body<3>> b = to_vec<3>(bodies_aos, n);
+        auto t0 = clk::now();
+        std::vector<Vector<3>> f = bvh_seq_n_body<3>(b);
+        auto t1 = clk::now();
+        if (forces_out) store<3>(f, forces_out);
+        return std::chrono::duration<double>(t1 - t0).count();
+    } catch (...) {
+        return -2.0;
+    }
+}
+
 double ref_G(void) { return G; }  // utils.h:21
 int ref_omp_threads(void) { return omp_get_max_threads(); }
 int ref_parlay_workers(void) { return (int)parlay::num_workers(); }
