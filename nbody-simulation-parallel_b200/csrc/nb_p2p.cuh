@@ -8,9 +8,9 @@
 // and pairs with r^2 < 1e-10.  Sign, guards and G are run-time parameters.
 //
 // Layout: the bodies are gathered into LEAF ORDER on the device (planar FP64: x | y | (z) | m, leaf after leaf), so a
-// leaf is a contiguous run.  One CTA per target leaf: lane = target (32 at a time), the CTA's warps split the source
-// leaves of the leaf's neighbour list between them and stage each through shared memory; per-target partial sums of
-// the warps meet in shared memory and the force goes to its body's row of the output (a body is the target of
+// leaf is a contiguous run.  One CTA per target leaf: lane = target (up to 32 at a time; smaller leaves give the spare
+// lanes a share of the sources), the CTA's warps split the source leaves of the leaf's neighbour list between them and
+// stage each through shared memory; per-target partial sums of the warps meet in shared memory and the force goes to its body's row of the output (a body is the target of
 // exactly one leaf: no atomics).  All FP64: tree-code P2P is held to the same 1e-12 as the brute-force path.
 #pragma once
 #include "nb_common.cuh"
@@ -56,8 +56,14 @@ __global__ void __launch_bounds__(NB_P2P_BLOCK) nb_p2p_leaf_kernel(const NbP2PPa
     for (long long leaf = blockIdx.x; leaf < P.n_leaves; leaf += gridDim.x) {
         const long long t0 = P.leaf_off[leaf], t1 = P.leaf_off[leaf + 1];
         const long long nb0 = P.nbr_off[leaf], nb1 = P.nbr_off[leaf + 1];
-        for (long long tb = t0; tb < t1; tb += 32) {                  // 32 targets at a time: one per lane
-            const long long ti = tb + lane;
+        // a group of `tw` lanes (a power of two >= the targets at hand, at most 32) holds one target per lane; the 32 / tw
+        // groups of the warp split the staged sources between them (a 16-body leaf keeps both half-warps busy)
+        for (long long tb = t0; tb < t1; tb += 32) {
+            const int nt = (int)min(32LL, t1 - tb);
+            int tw = 1;
+            while (tw < nt) tw <<= 1;
+            const int js = 32 / tw, part = lane / tw;
+            const long long ti = tb + (lane & (tw - 1));
             const bool live = ti < t1;
             double xi[D], mi = 0.0, acc[D];
             long long bi = -1;
@@ -78,7 +84,7 @@ __global__ void __launch_bounds__(NB_P2P_BLOCK) nb_p2p_leaf_kernel(const NbP2PPa
                         s_body[warp][k] = P.lbody[sb + k];
                     }
                     __syncwarp();
-                    for (int k = 0; k < cnt; ++k) {
+                    for (int k = part; k < cnt; k += js) {
                         double dd[D], r2 = 0.0;
                         bool same = P.eps_same >= 0.0;
 #pragma unroll
@@ -96,11 +102,16 @@ __global__ void __launch_bounds__(NB_P2P_BLOCK) nb_p2p_leaf_kernel(const NbP2PPa
                     }
                 }
             }
+            // groups -> the group of part 0 (every lane takes part: the loop bounds above are lane dependent)
+            for (int o = tw; o < 32; o <<= 1) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
+            }
             // warps -> one sum per target
 #pragma unroll
             for (int d = 0; d < D; ++d) s_sum[warp][d][lane] = acc[d];
             __syncthreads();
-            if (warp == 0 && live) {
+            if (warp == 0 && live && part == 0) {
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     double v = 0.0;

@@ -27,10 +27,9 @@ f, ms = pkg.p2p_leaves_cuda(b, *lists, return_ms=True, **pkg.P2P_BVH)     # warm
 best = min(pkg.p2p_leaves_cuda(b, *lists, return_ms=True, **pkg.P2P_BVH)[1] for _ in range(3))
 # CPU: the first --cpu-leaves target leaves (their source lists reach into the rest), all host threads
 k = min(a.cpu_leaves, sizes.shape[0])
-sub = (np.concatenate([leaf_off[:k + 1], np.full(sizes.shape[0] - k, leaf_off[k])]), order,
-       np.concatenate([nbr_off[:k + 1], np.full(sizes.shape[0] - k, nbr_off[k])]), nbr)
+sub_nbr_off = np.concatenate([nbr_off[:k + 1], np.full(sizes.shape[0] - k, nbr_off[k])])     # later leaves: no sources
 t0 = time.perf_counter()
-ref = oracle.p2p_leaves(b, sub[0], order, sub[2], nbr, **{"cutoff": 1e-9, "eps_same": 1e-9})
+ref = oracle.p2p_leaves(b, leaf_off, order, sub_nbr_off, nbr, **{"cutoff": 1e-9, "eps_same": 1e-9})
 cpu_s = time.perf_counter() - t0
 cpu_pairs = float(sum(sizes[l] * sizes[nbr[nbr_off[l]:nbr_off[l + 1]]].sum() for l in range(k)))
 tg = order[:leaf_off[k]]
