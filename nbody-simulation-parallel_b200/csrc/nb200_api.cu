@@ -1750,7 +1750,7 @@ int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, do
         CK(cudaMemsetAsync(s.energy, 0, 2 * sizeof(double), s.compute));
         if (s.n_local > 0) {
             const int threads = 256;
-            const int blocks = (int)((s.n_local + threads - 1) / threads);
+            const int blocks = (int)((s.n_local + threads * NB_ENERGY_TI - 1) / (threads * NB_ENERGY_TI));
 #define NB_EN(DD, RR)                                                                                   \
     nb_energy_kernel<DD, RR><<<blocks, threads, 0, s.compute>>>(                                         \
         (const RR*)s.src[ctx->cur], ctx->ntiles, s.tgt_base, s.n_local, s.tpad, s.vel, s.mass, G, cs,    \

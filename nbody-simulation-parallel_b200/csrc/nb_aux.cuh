@@ -144,8 +144,12 @@ __global__ void nb_unpack_kernel(double* __restrict__ aos_rows, size_t stride_d,
 
 // Energy of the reference's own law in FP64: per own target i
 //   ke_i = 1/2 m_i v_i^2,   pe_i = (G m_i / 4) * sum_{j != i, r^2 >= cutoff} m_j / r^2
-// (pe summed over ordered pairs, hence 1/4 = 1/2 * 1/2).  Sources come from the tile-planar
-// buffer (float-rounded in FP32 mode, undone by inv_pos_scale / inv_mass_scale).
+// (pe summed over ordered pairs, hence 1/4 = 1/2 * 1/2).  Sources come from the tile-planar buffer (float-rounded
+// in FP32 mode, undone by inv_pos_scale / inv_mass_scale).  Same scaffold as the force pass on a small scale: a
+// source tile is staged once per CTA in its storage type, every thread keeps TWO targets in registers, the
+// reciprocal is MUFU.RCP64H + one cubic step (nb_rcp_f64) instead of a true divide, and the pair loop is 8 DP
+// operations per pair (3 DADD/DFMA for r^2 in 3D, 3 for 1/r^2, 1 DFMA for the sum, 1 DSETP for the cut-off).
+#define NB_ENERGY_TI 2
 template <int D, typename real>
 __global__ void __launch_bounds__(256) nb_energy_kernel(const real* __restrict__ src, long long ntiles,
                                                          long long tgt_base, long long n_local, int tpad,
@@ -155,45 +159,58 @@ __global__ void __launch_bounds__(256) nb_energy_kernel(const real* __restrict__
                                                          double inv_mass_scale,
                                                          double* __restrict__ out /* [2] ke, pe */) {
     constexpr int NP = D + 1;
-    __shared__ double tile[NB_TILE * NP];
+    __shared__ real tile[NB_TILE * NP];
     __shared__ double red[2][8];
-    const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = li < n_local;
-    const long long b = tgt_base + (active ? li : 0);
-    double xi[D];
-    const real* tb = src + (size_t)(b / NB_TILE) * (NB_TILE * NP) + (b % NB_TILE);
+    double xi[NB_ENERGY_TI][D], sum[NB_ENERGY_TI];
+    long long li[NB_ENERGY_TI];
 #pragma unroll
-    for (int d = 0; d < D; ++d) xi[d] = (double)tb[d * NB_TILE];
-    double sum = 0.0;
-    for (long long t = 0; t < ntiles; ++t) {
+    for (int t = 0; t < NB_ENERGY_TI; ++t) {
+        li[t] = ((long long)blockIdx.x * NB_ENERGY_TI + t) * blockDim.x + threadIdx.x;
+        const long long b = tgt_base + (li[t] < n_local ? li[t] : 0);
+        const real* tb = src + (size_t)(b / NB_TILE) * (NB_TILE * NP) + (b % NB_TILE);
+#pragma unroll
+        for (int d = 0; d < D; ++d) xi[t][d] = (double)tb[d * NB_TILE];
+        sum[t] = 0.0;
+    }
+    for (long long tl = 0; tl < ntiles; ++tl) {
         __syncthreads();
-        for (int k = threadIdx.x; k < NB_TILE * NP; k += blockDim.x)
-            tile[k] = (double)src[(size_t)t * (NB_TILE * NP) + k];
+        for (int k = threadIdx.x; k < NB_TILE * NP; k += blockDim.x) tile[k] = src[(size_t)tl * (NB_TILE * NP) + k];
         __syncthreads();
-#pragma unroll 4
+#pragma unroll 2
         for (int j = 0; j < NB_TILE; ++j) {
-            double r2 = 0.0;
+            double xj[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const double dd = tile[d * NB_TILE + j] - xi[d];
-                r2 = fma(dd, dd, r2);
+            for (int d = 0; d < D; ++d) xj[d] = (double)tile[d * NB_TILE + j];
+            const double mj = (double)tile[D * NB_TILE + j];
+#pragma unroll
+            for (int t = 0; t < NB_ENERGY_TI; ++t) {
+                double r2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const double dd = xj[d] - xi[t][d];
+                    r2 = fma(dd, dd, r2);
+                }
+                const bool keep = r2 >= cutoff_scaled;              // drops the self pair and duplicates as well (r2 = 0)
+                const double inv = nb_rcp_f64(keep ? r2 : 1.0);
+                sum[t] = fma(keep ? mj : 0.0, inv, sum[t]);
             }
-            const double inv = (r2 >= cutoff_scaled) ? 1.0 / r2 : 0.0;
-            sum = fma(tile[D * NB_TILE + j], inv, sum);
         }
     }
     double ke = 0.0, pe = 0.0;
-    if (active) {
-        const double m = mass[li];
-        double v2 = 0.0;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const double v = vel[(size_t)d * tpad + li];
-            v2 = fma(v, v, v2);
+    for (int t = 0; t < NB_ENERGY_TI; ++t) {
+        if (li[t] < n_local) {
+            const double m = mass[li[t]];
+            double v2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const double v = vel[(size_t)d * tpad + li[t]];
+                v2 = fma(v, v, v2);
+            }
+            ke += 0.5 * m * v2;
+            // sum is in scaled units: m' / r'^2 = (m ms) / (r^2 ps^2)
+            pe += 0.25 * G * m * sum[t] * inv_mass_scale / (inv_pos_scale * inv_pos_scale);
         }
-        ke = 0.5 * m * v2;
-        // sum is in scaled units: m' / r'^2 = (m ms) / (r^2 ps^2)
-        pe = 0.25 * G * m * sum * inv_mass_scale / (inv_pos_scale * inv_pos_scale);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
