@@ -432,6 +432,8 @@ def run_product_arm(args) -> None:
     n, prec, DIM, DT = cfg["n"], args.precision, cfg["dim"], cfg["dt"]
     bodies = make_bodies(pkg.generators, cfg)
     oracle = entry.load_oracle() if (rank == 0 and not args.no_parity) else None    # checker only, after the timed region
+    if oracle is not None and world > 1:
+        oracle.set_num_threads(max(1, (os.cpu_count() or 1) // 2))   # torchrun pinned OMP_NUM_THREADS=1; only rank 0 runs the checker
 
     def bcast_ok(flag: bool) -> bool:
         if world == 1:

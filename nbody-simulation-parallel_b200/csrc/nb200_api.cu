@@ -226,7 +226,7 @@ struct nb200_ctx {
     bool image_full = true;       // the staging image holds all n bodies (false: only the rows each shard owns)
     bool dead = false;            // a peer handshake timed out: the ranks' step counters may have diverged
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0, opt_seg_sub = 0, opt_shard_upload = -1;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0, opt_seg_sub = 0, opt_shard_upload = -1, opt_pdl = -1;
     long opt_spin_timeout_ms = 30000;   // bound of every device-side wait on a peer's flag
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
@@ -764,6 +764,24 @@ int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg_sub, int seg_ord, int subt,
     return NB200_OK;
 }
 
+// Launch with programmatic dependent launch allowed: the kernel may start (and run its prologue) while its predecessor in
+// the stream drains; it waits for the predecessor itself (nb_grid_dep_wait).  A step of a small problem is two short
+// launches back to back: the launch latency between them is the part of the step this hides.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // symmetric force kernel, [push of the reaction sums to their owners], finish kernel (forces or integrate)
 int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff, double dt, int cur, bool with_flags,
                      const Handshake& hs = Handshake()) {
@@ -832,8 +850,9 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     Q.total_units = s.sym_prefix_host.back();
     Q.cutoff = cutoff * ctx->pos_scale * ctx->pos_scale;
     const int grid = std::min(resident, Q.total_units);
-    kfn<<<grid, block, smem, s.compute>>>(Q);
-    CK(cudaGetLastError());
+    // one shard, no pre-pass: the step is this pass + the finish kernel, chained by programmatic dependent launch
+    const bool pdl = !cross && ctx->world == 1 && ctx->opt_pdl != 0;
+    CK(launch_pdl(kfn, grid, block, smem, s.compute, pdl && !with_flags, Q));
     ctx->launches++;
 
     NbSymFinish F;
@@ -879,13 +898,12 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     NbForceParams P = base_params(ctx, s, mode, G, cutoff, dt, cur, hs);
     const int fb = (s.tpad + 255) / 256;
     if (ctx->f64) {
-        if (D == 3) nb_finish_kernel<3, double><<<fb, 256, 0, s.compute>>>(P, F);
-        else nb_finish_kernel<2, double><<<fb, 256, 0, s.compute>>>(P, F);
+        if (D == 3) CK(launch_pdl(nb_finish_kernel<3, double>, fb, 256, 0, s.compute, pdl, P, F));
+        else CK(launch_pdl(nb_finish_kernel<2, double>, fb, 256, 0, s.compute, pdl, P, F));
     } else {
-        if (D == 3) nb_finish_kernel<3, float><<<fb, 256, 0, s.compute>>>(P, F);
-        else nb_finish_kernel<2, float><<<fb, 256, 0, s.compute>>>(P, F);
+        if (D == 3) CK(launch_pdl(nb_finish_kernel<3, float>, fb, 256, 0, s.compute, pdl, P, F));
+        else CK(launch_pdl(nb_finish_kernel<2, float>, fb, 256, 0, s.compute, pdl, P, F));
     }
-    CK(cudaGetLastError());
     ctx->launches++;
     if (&s == &ctx->shards[0]) {
         char buf[320];
@@ -1407,6 +1425,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "variant")) ctx->opt_variant = (value >= 0 && value < kNumVariants) ? (int)value : -1;
     else if (!strcmp(key, "seg_tiles")) ctx->opt_seg_tiles = (int)std::max(0L, value);
     else if (!strcmp(key, "seg_sub")) ctx->opt_seg_sub = (int)std::max(0L, value);
+    else if (!strcmp(key, "pdl")) ctx->opt_pdl = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "shard_upload")) ctx->opt_shard_upload = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);
     else if (!strcmp(key, "overlap")) ctx->opt_overlap = value < 0 ? -1 : (value != 0);

@@ -121,6 +121,13 @@ __device__ __forceinline__ void nb_st_release_sys(unsigned long long* p, unsigne
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may
+// start while its predecessor in the stream still runs; nb_grid_dep_wait() blocks until that predecessor has
+// completed and its writes are visible, nb_launch_dependents() lets the successor begin launching.  Both are
+// no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void nb_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void nb_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long nb_globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -586,6 +586,7 @@ nb_force_sym_kernel(const NbSymParams P) {
     const real* __restrict__ src = static_cast<const real*>(P.src);
     float* scr = scr_all + (size_t)warp * 2 * 32 * NB_SYM_ROW;
 
+    nb_launch_dependents();   // the finish kernel behind this pass may queue up (it waits for the pass's completion itself)
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             nb_mbar_init(&full_bar[s], 1);
@@ -594,6 +595,7 @@ nb_force_sym_kernel(const NbSymParams P) {
         nb_fence_mbar_init();
     }
     __syncthreads();
+    nb_grid_dep_wait();       // sources, accumulators and the unit counter come from the kernels before this one
 
     unsigned kt = 0;          // tiles consumed by this CTA so far (ring position)
     int bbuf = 0;             // which half of bout the next symmetric tile writes
@@ -831,6 +833,8 @@ __global__ void __launch_bounds__(256) nb_sym_push_kernel(const NbSymPush Q) {
 template <int D, typename real>
 __global__ void __launch_bounds__(256) nb_finish_kernel(const NbForceParams P, const NbSymFinish F) {
     constexpr int NP = D + 1;
+    nb_grid_dep_wait();       // the pass before this kernel is complete and visible
+    nb_launch_dependents();   // the next step's pass may queue up behind this kernel (it waits for it itself)
     if (F.seq != 0ull && F.n_src > 0) {
         if (threadIdx.x < F.n_src)
             nb_wait_flag(F.flag[threadIdx.x], F.seq, P.spin_timeout_ns, P.err_word, NB_WAIT_REACTION, F.sender[threadIdx.x]);

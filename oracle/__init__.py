@@ -80,6 +80,8 @@ class _Oracle:
         L.oracle_accuracy_pct.argtypes = [ctypes.c_int, sz, _dp, _dp]
         L.oracle_accuracy_pct.restype = ctypes.c_double
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_num_threads.argtypes = [ctypes.c_int]
+        L.oracle_set_num_threads.restype = None
 
 
 _oracle = None
@@ -196,6 +198,11 @@ def accuracy_pct(forces_, reference):
 
 def num_threads():
     return _o().oracle_num_threads()
+
+
+def set_num_threads(n: int):
+    """Checker threads (torchrun pins OMP_NUM_THREADS=1 for its workers)."""
+    _o().oracle_set_num_threads(int(n))
 
 
 # --------------------------------------------------------------------------- the real reference

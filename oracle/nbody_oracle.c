@@ -399,3 +399,13 @@ int oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* torchrun pins OMP_NUM_THREADS=1 for its workers; the checker on rank 0 may take more threads back */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
