@@ -150,7 +150,7 @@ struct Shard {
     double *acc = nullptr, *pos = nullptr, *vel = nullptr, *mass = nullptr, *forces = nullptr;
     double* aos_dev = nullptr;            // staging image of the AoS bodies (upload/download)
     size_t aos_bytes = 0;
-    unsigned long long* bounds = nullptr; // [2] bit patterns of max |coordinate|, max |mass| of the image
+    unsigned long long* bounds = nullptr; // [3] bit patterns of max |coordinate|, max |mass|, min |mass| of the image
     double* energy = nullptr;             // [2]
     double* cmp = nullptr;                // [2][n_local*D] staging of host force arrays for nb200_accuracy_pct
     bool forces_valid = false;            // s.forces holds the result of the last nb200_forces call
@@ -188,7 +188,7 @@ constexpr int kSymMaxSlots = kMaxWorldP2P / 2;      // senders of reaction sums 
 // ready; one per writer rank each), the per-rank bounds table of a shard-local upload (2 words per rank), then the
 // receive slots of the pair-symmetric pass.
 constexpr size_t kFlagsBytes = 512;
-constexpr int kBoundsTableWord = 4 * (NB_MAX_PEERS + 1);
+constexpr int kBoundsTableWord = 4 * (NB_MAX_PEERS + 1);          // 3 words per rank: 32 + 24 <= 64 words
 // The 256-target i-tile shape is opt-in only ("sym_itile" option): measured, it never beats the 1024
 // shape nor, below N ~ 32768, the ordered pass (N=16384: 1414 vs 1454 vs 1994 G inter/s).
 constexpr size_t kSymSmallN = 0;
@@ -224,9 +224,11 @@ struct nb200_ctx {
     std::vector<unsigned long long> acc_seq_issued;   // per driven shard: pair-symmetric passes with a reaction exchange so far
     bool pristine = false;        // no step since the last upload: the AoS staging image is still current
     bool image_full = true;       // the staging image holds all n bodies (false: only the rows each shard owns)
+    bool equal_mass = false;      // every body has the same (positive) mass: the pair kernels run without the masses
+    double common_mass = 0.0;
     bool dead = false;            // a peer handshake timed out: the ranks' step counters may have diverged
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0, opt_seg_sub = 0, opt_shard_upload = -1, opt_pdl = -1;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0, opt_seg_sub = 0, opt_shard_upload = -1, opt_pdl = -1, opt_eqm = -1;
     long opt_spin_timeout_ms = 30000;   // bound of every device-side wait on a peer's flag
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
@@ -286,7 +288,19 @@ template <int D, bool F64> SymKernel sym_kernel_of(SymShape sh, int algo) {
     if constexpr (!F64) { if (algo == 2) return sym_kernel_of<D, false, 2>(sh); }
     return sym_kernel_of<D, F64, 0>(sh);
 }
-SymKernel pick_sym_kernel(int dim, bool f64, SymShape sh, int algo) {
+// The equal-mass flavour exists for the default shapes and reduction only (FP32: 8 x 128 and 4 x 128 with the decoupled
+// rotation; FP64: 4 x 256 with the rotation); every other combination runs the general kernels, which are correct for
+// equal masses too.
+bool sym_has_eqm(bool f64, SymShape sh, int algo) {
+    if (f64) return algo == 1 && sh.ti == 4 && sh.block == 256;
+    return algo == 2 && sh.block == 128 && (sh.ti == 8 || sh.ti == 4);
+}
+template <int D> SymKernel sym_kernel_eqm(bool f64, SymShape sh) {
+    if (f64) return nb_force_sym_kernel<D, true, 4, 256, 1, true>;
+    return sh.ti == 8 ? nb_force_sym_kernel<D, false, 8, 128, 2, true> : nb_force_sym_kernel<D, false, 4, 128, 2, true>;
+}
+SymKernel pick_sym_kernel(int dim, bool f64, SymShape sh, int algo, bool eqm = false) {
+    if (eqm && sym_has_eqm(f64, sh, algo)) return dim == 3 ? sym_kernel_eqm<3>(f64, sh) : sym_kernel_eqm<2>(f64, sh);
     if (dim == 3) return f64 ? sym_kernel_of<3, true>(sh, algo) : sym_kernel_of<3, false>(sh, algo);
     return f64 ? sym_kernel_of<2, true>(sh, algo) : sym_kernel_of<2, false>(sh, algo);
 }
@@ -344,7 +358,7 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
     s.aos_bytes = std::max<size_t>(1, ctx->n) * (size_t)(2 * D + 1) * sizeof(double);
     CK(cudaMalloc(&s.aos_dev, s.aos_bytes));
     CK(cudaMalloc(&s.energy, 2 * sizeof(double)));
-    CK(cudaMalloc(&s.bounds, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&s.bounds, 3 * sizeof(unsigned long long)));
     CK(cudaMalloc(&s.tile_done, (tp / 32 + 1) * sizeof(unsigned)));
     CK(cudaMemset(s.tile_done, 0, (tp / 32 + 1) * sizeof(unsigned)));
     {
@@ -388,6 +402,11 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
         for (int algo = 0; algo <= (sh.block == 64 ? 0 : ctx->f64 ? 1 : 2); ++algo)
             CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, sh, algo), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo)));
+    for (const SymShape& sh : ctx->f64 ? kSymShapesF64 : kSymShapesF32)
+        for (int algo = 1; algo <= 2; ++algo)
+            if (sym_has_eqm(ctx->f64, sh, algo))
+                CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, sh, algo, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo)));
     return preload_aux_kernels(ctx);
 }
 
@@ -529,7 +548,9 @@ int nsegs(int b, int e, int seg) { return e > b ? (e - b + seg - 1) / seg : 0; }
 // suspect flag of every own (padded) target.  Reads src[cur], so it runs after the peer handshake.
 int launch_detect(nb200_ctx* ctx, Shard& s, double cutoff, int cur) {
     const int D = ctx->dim;
-    const long long nbodies = ctx->ntiles * NB_TILE;
+    // every source takes part in the grid, the zero-mass padding included (it sits on a real body's position); parked
+    // padding (equal-mass systems) is out of range of everything and stays out of the grid
+    const long long nbodies = ctx->equal_mass ? (long long)ctx->n : ctx->ntiles * NB_TILE;
     const double cs = cutoff * ctx->pos_scale * ctx->pos_scale;
     NbGrid g;
     g.keys = s.grid_keys;
@@ -583,12 +604,10 @@ __global__ void nb_wait_flags_kernel(const unsigned long long* flags, int stride
 __global__ void nb_publish_ready_kernel(NbForceParams P, const unsigned long long* my_bounds, int table_word, int ready_word,
                                         unsigned long long epoch) {
     if (threadIdx.x == 0) {
-        const unsigned long long bx = my_bounds[0], bm = my_bounds[1];
-        P.my_flags[table_word + 2 * P.my_rank] = bx;
-        P.my_flags[table_word + 2 * P.my_rank + 1] = bm;
-        for (int p = 0; p < P.n_peers; ++p) {
-            P.peer_flags[p][table_word + 2 * P.my_rank] = bx;
-            P.peer_flags[p][table_word + 2 * P.my_rank + 1] = bm;
+        for (int k = 0; k < 3; ++k) {                 // max |x|, max |m|, min |m| of the own rows
+            const unsigned long long v = my_bounds[k];
+            P.my_flags[table_word + 3 * P.my_rank + k] = v;
+            for (int p = 0; p < P.n_peers; ++p) P.peer_flags[p][table_word + 3 * P.my_rank + k] = v;
         }
         __threadfence_system();
         for (int p = 0; p < P.n_peers; ++p) nb_st_release_sys(P.peer_flags[p] + ready_word + P.my_rank, epoch);
@@ -829,7 +848,8 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     const int ti = sh.ti, block = sh.block;
     const int itile = ti * block;
     const int seg_ord = std::max(1, seg_sub / subt);
-    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, sh, algo);
+    const bool eqm = ctx->equal_mass && sym_has_eqm(ctx->f64, sh, algo);
+    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, sh, algo, eqm);
     const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64, ti, algo);
     if (int rc = build_sym_rows(ctx, s, seg_sub, seg_ord, subt, cross, itile / NB_TILE)) return rc;
     const int seg = seg_sub;
@@ -896,6 +916,7 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
         ctx->launches++;
     }
     NbForceParams P = base_params(ctx, s, mode, G, cutoff, dt, cur, hs);
+    if (eqm) P.acc_scale *= ctx->common_mass * ctx->mass_scale;      // the pass summed without the (common) mass
     const int fb = (s.tpad + 255) / 256;
     if (ctx->f64) {
         if (D == 3) CK(launch_pdl(nb_finish_kernel<3, double>, fb, 256, 0, s.compute, pdl, P, F));
@@ -913,6 +934,7 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
                  mode ? "step" : "forces", ctx->f64 ? 64 : 32, D, ctx->n, ctx->world, ti, block, itile, algo, seg, subt, Q.n_rows, Q.total_units, grid,
                  ctx->ntiles, with_flags ? "grid-prepass(plain|exact)" : "exact",
                  cross ? " + reaction sums pushed to their owners over NVLink" : "");
+        if (eqm) strncat(buf, " [equal-mass chains]", sizeof buf - strlen(buf) - 1);
         ctx->plan = buf;
     }
     return NB200_OK;
@@ -1001,7 +1023,7 @@ int pack_sources(nb200_ctx* ctx) {
 #define NB_PACK(DD, RR)                                                                              \
     nb_pack_kernel<DD, RR><<<blocks, threads, 0, s.compute>>>(                                       \
         s.aos_dev, sd, (long long)ctx->n, ctx->nalloc, (RR*)s.src[0], (RR*)s.src[1], ctx->pos_scale, \
-        ctx->mass_scale, s.tgt_base, s.tpad, s.pos, s.vel, s.mass)
+        ctx->mass_scale, s.tgt_base, s.tpad, s.pos, s.vel, s.mass, ctx->equal_mass ? 1 : 0)
             if (D == 3) { if (ctx->f64) NB_PACK(3, double); else NB_PACK(3, float); }
             else        { if (ctx->f64) NB_PACK(2, double); else NB_PACK(2, float); }
 #undef NB_PACK
@@ -1016,7 +1038,7 @@ int pack_sources(nb200_ctx* ctx) {
 #define NB_PACK(DD, RR)                                                                                              \
     nb_pack_shard_kernel<DD, RR><<<blocks, threads, 0, s.compute>>>(                                                 \
         s.aos_dev, sd, (long long)ctx->n, s.tgt_base, span, s.tpad, nbodies, ctx->nalloc, (RR*)s.src[0], (RR*)s.src[1], pb, \
-        ctx->pos_scale, ctx->mass_scale, s.pos, s.vel, s.mass)
+        ctx->pos_scale, ctx->mass_scale, s.pos, s.vel, s.mass, ctx->equal_mass ? 1 : 0)
             if (D == 3) { if (ctx->f64) NB_PACK(3, double); else NB_PACK(3, float); }
             else        { if (ctx->f64) NB_PACK(2, double); else NB_PACK(2, float); }
 #undef NB_PACK
@@ -1117,7 +1139,9 @@ int publish_epoch(nb200_ctx* ctx) {
     return NB200_OK;
 }
 
-void set_fp32_scales(nb200_ctx* ctx, double xmax, double mmax) {
+void set_fp32_scales(nb200_ctx* ctx, double xmax, double mmax, double mmin) {
+    ctx->equal_mass = ctx->opt_eqm != 0 && ctx->n > 0 && mmax > 0.0 && isfinite(mmax) && mmin == mmax;
+    ctx->common_mass = ctx->equal_mass ? mmax : 0.0;
     int ex = 0;
     if (xmax > 0 && isfinite(xmax)) ctx->xmax = xmax;
     if (!ctx->f64) {
@@ -1138,6 +1162,7 @@ int shard_local_bounds(nb200_ctx* ctx) {
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
         CK(cudaMemsetAsync(s.bounds, 0, 2 * sizeof(unsigned long long), s.compute));
+        CK(cudaMemsetAsync(s.bounds + 2, 0xFF, sizeof(unsigned long long), s.compute));     // min |mass|: all ones = no body yet
         if (s.n_local > 0) {
             const int blocks = (int)std::min<long long>(4LL * s.sms, (s.n_local + 255) / 256);
             const double* rows = s.aos_dev + (size_t)s.tgt_base * sd;
@@ -1156,13 +1181,13 @@ int shard_local_bounds(nb200_ctx* ctx) {
         CK(cudaGetLastError());
         ctx->launches++;
     }
-    double xmax = 0.0, mmax = 0.0;
+    double xmax = 0.0, mmax = 0.0, mmin = HUGE_VAL;
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
         nb_wait_ready_kernel<<<1, 32, 0, s.compute>>>(s.flags, ready_word, s.n_peers, PeerRanks(s), next_epoch, timeout_ns, s.err_dev);
         CK(cudaGetLastError());
         ctx->launches++;
-        double table[2 * kMaxWorldP2P];
+        double table[3 * kMaxWorldP2P];
         CK(cudaMemcpyAsync(table, s.flags + kBoundsTableWord, sizeof table, cudaMemcpyDeviceToHost, s.compute));
         CK(cudaStreamSynchronize(s.compute));
         if (s.err_host && *reinterpret_cast<volatile unsigned long long*>(s.err_host)) {
@@ -1172,11 +1197,12 @@ int shard_local_bounds(nb200_ctx* ctx) {
                         s.rank, next_epoch, ctx->opt_spin_timeout_ms);
         }
         for (int r = 0; r < ctx->world && r < kMaxWorldP2P; ++r) {
-            if (table[2 * r] > xmax) xmax = table[2 * r];
-            if (table[2 * r + 1] > mmax) mmax = table[2 * r + 1];
+            if (table[3 * r] > xmax) xmax = table[3 * r];
+            if (table[3 * r + 1] > mmax) mmax = table[3 * r + 1];
+            if (table[3 * r + 2] < mmin) mmin = table[3 * r + 2];      // an empty shard holds all ones = NaN: never smaller
         }
     }
-    set_fp32_scales(ctx, xmax, mmax);
+    set_fp32_scales(ctx, xmax, mmax, mmin);
     return NB200_OK;
 }
 
@@ -1191,15 +1217,18 @@ int finish_upload(nb200_ctx* ctx) {
         Shard& s = ctx->shards[0];
         CK(cudaSetDevice(s.device));
         CK(cudaMemsetAsync(s.bounds, 0, 2 * sizeof(unsigned long long), s.compute));
+        CK(cudaMemsetAsync(s.bounds + 2, 0xFF, sizeof(unsigned long long), s.compute));
         const int blocks = (int)std::min<long long>(4LL * s.sms, ((long long)ctx->n + 255) / 256);
         if (D == 3) nb_bounds_kernel<3><<<blocks, 256, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, s.bounds);
         else nb_bounds_kernel<2><<<blocks, 256, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, s.bounds);
         CK(cudaGetLastError());
         ctx->launches++;
-        double hb[2] = {0.0, 0.0};
+        double hb[3] = {0.0, 0.0, 0.0};
         CK(cudaMemcpyAsync(hb, s.bounds, sizeof hb, cudaMemcpyDeviceToHost, s.compute));
         CK(cudaStreamSynchronize(s.compute));
-        set_fp32_scales(ctx, hb[0], hb[1]);
+        set_fp32_scales(ctx, hb[0], hb[1], hb[2]);
+    } else {
+        ctx->equal_mass = false;
     }
     int rc = pack_sources(ctx);
     if (rc) return rc;
@@ -1425,6 +1454,12 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "variant")) ctx->opt_variant = (value >= 0 && value < kNumVariants) ? (int)value : -1;
     else if (!strcmp(key, "seg_tiles")) ctx->opt_seg_tiles = (int)std::max(0L, value);
     else if (!strcmp(key, "seg_sub")) ctx->opt_seg_sub = (int)std::max(0L, value);
+    else if (!strcmp(key, "equal_mass")) {
+        // 0 switches the equal-mass flavour of the pair kernels off; the padding layout is fixed at upload, so set it before
+        if (ctx->uploaded && (value != 0) != (ctx->opt_eqm != 0))
+            return fail(ctx, NB200_ESTATE, "set 'equal_mass' before the upload (it decides where the padding bodies go)");
+        ctx->opt_eqm = value < 0 ? -1 : (value != 0);
+    }
     else if (!strcmp(key, "pdl")) ctx->opt_pdl = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "shard_upload")) ctx->opt_shard_upload = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);

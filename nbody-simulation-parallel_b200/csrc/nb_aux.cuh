@@ -2,6 +2,14 @@
 #pragma once
 #include "nb_common.cuh"
 
+// Equal-mass systems run the pair kernels without the masses (nb_force_sym.cuh, EQM), so a padding body cannot be
+// silenced by its zero mass: it is parked out of range instead, where 1/r^4 underflows to exactly 0 against every real
+// body (FP32: r^2 ~ 1e30, FP64: 1e300; distinct per body, so padding never coincides with padding).
+template <typename real> __device__ __forceinline__ real nb_park_coordinate(long long b) {
+    const double far = sizeof(real) == 8 ? 1.0e150 : 1.0e15;
+    return (real)(far * (1.5 + (double)(b & 1023) / 1024.0));     // never the 1.0 * far the force kernel parks idle lanes at
+}
+
 // AoS Body<D> (body.h:7-19; stride_d doubles per body) -> tile-planar sources for ALL bodies of
 // both ring buffers, plus the FP64 master state of the own targets.  Padding bodies (index >= n)
 // get mass 0 and the position of body 0: every pair with them contributes exactly 0.
@@ -10,7 +18,7 @@ __global__ void nb_pack_kernel(const double* __restrict__ aos, size_t stride_d, 
                                long long nalloc, real* __restrict__ src0, real* __restrict__ src1,
                                double pos_scale, double mass_scale, long long tgt_base, int tpad,
                                double* __restrict__ pos, double* __restrict__ vel,
-                               double* __restrict__ mass) {
+                               double* __restrict__ mass, int park) {
     constexpr int NP = D + 1;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nalloc) return;
@@ -22,7 +30,7 @@ __global__ void nb_pack_kernel(const double* __restrict__ aos, size_t stride_d, 
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         x[d] = (n > 0) ? rec[d] : 0.0;
-        const real xs = (real)(x[d] * pos_scale);
+        const real xs = (park && !real_body) ? nb_park_coordinate<real>(b) : (real)(x[d] * pos_scale);
         d0[d * NB_TILE] = xs;
         d1[d * NB_TILE] = xs;
     }
@@ -55,7 +63,7 @@ __global__ void nb_pack_shard_kernel(const double* __restrict__ aos, size_t stri
                                      int span, int tpad, long long nbodies, long long nalloc,
                                      real* __restrict__ src0, real* __restrict__ src1, NbPeerBufs peers,
                                      double pos_scale, double mass_scale, double* __restrict__ pos,
-                                     double* __restrict__ vel, double* __restrict__ mass) {
+                                     double* __restrict__ vel, double* __restrict__ mass, int park) {
     constexpr int NP = D + 1;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool slack = t >= tpad;
@@ -74,7 +82,8 @@ __global__ void nb_pack_shard_kernel(const double* __restrict__ aos, size_t stri
         const size_t off = (size_t)(b / NB_TILE) * (NB_TILE * NP) + (b % NB_TILE);
 #pragma unroll
         for (int d = 0; d <= D; ++d) {
-            const real v = d < D ? (real)(x[d] * pos_scale) : (real)(m * mass_scale);
+            const real v = d < D ? ((park && !real_body) ? nb_park_coordinate<real>(b) : (real)(x[d] * pos_scale))
+                                 : (real)(m * mass_scale);
             src0[off + (size_t)d * NB_TILE] = v;
             src1[off + (size_t)d * NB_TILE] = v;
             if (own_row)
@@ -94,13 +103,13 @@ __global__ void nb_pack_shard_kernel(const double* __restrict__ aos, size_t stri
     }
 }
 
-// max |coordinate| and max |mass| over the AoS image (FP32 mode picks its power-of-two source
-// scales from them).  Non-negative doubles order like their bit patterns, so the reduction ends
+// max |coordinate|, max |mass| and min |mass| over the AoS image (FP32 mode picks its power-of-two source
+// scales from the first two; min == max marks an equal-mass system).  Non-negative doubles order like their bit patterns, so the reduction ends
 // in one 64-bit atomicMax per warp.  NaNs are ignored (every comparison with them is false).
 template <int D>
 __global__ void __launch_bounds__(256) nb_bounds_kernel(const double* __restrict__ aos, size_t stride_d,
                                                          long long n, unsigned long long* __restrict__ out) {
-    double xm = 0.0, mm = 0.0;
+    double xm = 0.0, mm = 0.0, mlo = __longlong_as_double(0x7ff0000000000000ll);      // +inf
     for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < n;
          b += (long long)gridDim.x * blockDim.x) {
         const double* rec = aos + (size_t)b * stride_d;
@@ -111,19 +120,24 @@ __global__ void __launch_bounds__(256) nb_bounds_kernel(const double* __restrict
         }
         const double m = fabs(rec[2 * D]);
         if (m > mm) mm = m;
+        if (m < mlo) mlo = m;
     }
     unsigned long long xb = (unsigned long long)__double_as_longlong(xm);
     unsigned long long mb = (unsigned long long)__double_as_longlong(mm);
+    unsigned long long lb = (unsigned long long)__double_as_longlong(mlo);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long x2 = __shfl_xor_sync(0xffffffffu, xb, o);
         const unsigned long long m2 = __shfl_xor_sync(0xffffffffu, mb, o);
+        const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lb, o);
         xb = x2 > xb ? x2 : xb;
         mb = m2 > mb ? m2 : mb;
+        lb = l2 < lb ? l2 : lb;
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMax(&out[0], xb);
         atomicMax(&out[1], mb);
+        atomicMin(&out[2], lb);              // out[2] starts at all ones
     }
 }
 
@@ -258,6 +272,8 @@ __device__ __forceinline__ unsigned nb_slot_of(unsigned long long key, unsigned 
 
 template <int D, typename real>
 __global__ void nb_grid_insert_kernel(const real* __restrict__ src, long long nbodies, NbGrid g) {
+    // nbodies: every source incl. the zero-mass padding that sits on a real body's position; with parked padding
+    // (equal-mass systems) only the real bodies
     constexpr int NP = D + 1;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbodies) return;

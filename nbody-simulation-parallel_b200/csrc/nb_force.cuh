@@ -46,7 +46,9 @@ enum { NB_PLAIN = 0, NB_TRACKED = 1, NB_EXACT = 2 };
 #define NB_STR_(x) #x
 #define NB_UNROLL(n) _Pragma(NB_STR_(unroll n))
 
-template <int D, int TI, int JS, int MODE, int UNR>
+// EQM (equal-mass system, see nb_force_sym.cuh): the sums are taken WITHOUT the source masses (s = 1/r^4), the common
+// mass is applied once per body in the epilogue.
+template <int D, int TI, int JS, int MODE, int UNR, bool EQM = false>
 __device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, int part, float cutoff,
                                              const float (&npos)[TI][3], float2 (&a)[TI][3]) {
     const float4* sx = reinterpret_cast<const float4*>(stage);
@@ -92,7 +94,7 @@ __device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, in
                 inv.x = nb_rcp_f32(r2.x);
                 inv.y = nb_rcp_f32(r2.y);
                 float2 s = __fmul2_rn(inv, inv);
-                s = __fmul2_rn(s, ms);
+                if (!EQM) s = __fmul2_rn(s, ms);
                 a[t][0] = __ffma2_rn(s, dx, a[t][0]);
                 a[t][1] = __ffma2_rn(s, dy, a[t][1]);
                 if (D == 3) a[t][2] = __ffma2_rn(s, dz, a[t][2]);
@@ -103,7 +105,7 @@ __device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, in
 }
 
 // FP64: one tile against TI targets (pos holds the plain target coordinates).
-template <int D, int TI, int JS, bool EXACT>
+template <int D, int TI, int JS, bool EXACT, bool EQM = false>
 __device__ __forceinline__ void nb_tile_f64(const double* __restrict__ stage, int part, double cutoff,
                                             const double (&pos)[TI][3], double (&accd)[TI][3]) {
     const double2* sx = reinterpret_cast<const double2*>(stage);
@@ -132,7 +134,7 @@ __device__ __forceinline__ void nb_tile_f64(const double* __restrict__ stage, in
                 }
                 double inv = nb_rcp_f64(r2);
                 if (EXACT) inv = (r2 >= cutoff) ? inv : 0.0;  // drop (also kills the NaN of r2 = 0)
-                const double s = ms * (inv * inv);
+                const double s = EQM ? inv * inv : ms * (inv * inv);
                 accd[t][0] = fma(s, dx, accd[t][0]);
                 accd[t][1] = fma(s, dy, accd[t][1]);
                 if (D == 3) accd[t][2] = fma(s, dz, accd[t][2]);

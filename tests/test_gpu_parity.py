@@ -294,6 +294,27 @@ def test_baseline_config_sizes_default_path(pkg, oracle, name, dim, n, dist, see
     assert np.abs(f.sum(axis=0)).max() <= (1e-9 if prec == 64 else 1e-5) * np.abs(f).sum(axis=0).max()
 
 
+@pytest.mark.parametrize("dim,med,p99,worst,acc", [(3, 2e-5, 2e-4, 1e-2, 99.9), (2, 1e-4, 2e-3, 1e-1, 99.0)])
+def test_fp32_against_the_reference_on_unrounded_inputs(pkg, oracle, dim, med, p99, worst, acc):
+    """What FP32 mode costs against the reference on IDENTICAL (unrounded) double inputs in the reference's own range
+    (pos U[1,1e7], utils.h:113-115): the 24-bit quantisation of the positions moves every near-neighbour term by
+    ~4 * 2^-24 * |x| / r (include/nb200.h).  The bounds asserted here are that statement in numbers at N = 65536 --
+    median, 99th percentile, maximum of the per-body norm-wise error, and the reference's own 1 % criterion
+    (compute_accuracy_omp, utils.h:170-219) -- measured with 3-5x head room; FP64 mode on the same inputs holds 1e-12."""
+    n = 65536
+    b = pkg.generators.reference_range(n, dim, seed=77)
+    ref = oracle.forces(b)
+    with pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as ctx:
+        ctx.upload(b)                                   # unrounded doubles in: quantised by the library
+        f = ctx.forces()
+        pct = ctx.accuracy_pct(None, ref)
+    e = rel(pkg, f, ref)
+    assert np.median(e) <= med and np.percentile(e, 99) <= p99 and e.max() <= worst, (np.median(e), np.percentile(e, 99), e.max())
+    assert pct >= acc, pct
+    e64 = rel(pkg, pkg.brute_force_cuda_n_body(b, pkg.NB200_FP64), ref)
+    assert e64.max() <= TOL64
+
+
 def test_fp32_full_population_error_on_the_device(pkg, oracle):
     """nb200_compare_forces: FP32-mode forces of ALL bodies against an FP64 context on the same
     float-quantised inputs (histogram by decade, maximum).  At N = 65536 the full CPU oracle is still
@@ -413,9 +434,20 @@ def test_peer_handshake_timeout_returns_estate(pkg):
     import time
     n = 3000
     b = pkg.generators.uniform_cube(n, 3, seed=8)
+    # a shard-local upload is collective: the peer that never enters it is reported by the upload itself
     with pkg.NBodyCuda(3, n, pkg.NB200_FP64, rank=0, world=2, device=0) as ctx:
         ctx.set_option("debug_fake_peer", 1)
         ctx.set_option("spin_timeout_ms", 150)
+        t0 = time.perf_counter()
+        with pytest.raises(pkg.NB200Error, match=r"did not enter upload"):
+            ctx.upload(b)
+        assert time.perf_counter() - t0 < 10.0
+        with pytest.raises(pkg.NB200Error, match="unusable"):
+            ctx.upload(b)
+    with pkg.NBodyCuda(3, n, pkg.NB200_FP64, rank=0, world=2, device=0) as ctx:
+        ctx.set_option("debug_fake_peer", 1)
+        ctx.set_option("spin_timeout_ms", 150)
+        ctx.set_option("shard_upload", 0)                # every rank uploads everything: no handshake at upload
         ctx.upload(b)
         t0 = time.perf_counter()
         with pytest.raises(pkg.NB200Error, match=r"peer 1 did not publish"):
@@ -686,6 +718,54 @@ def test_pair_symmetric_subtile_units_and_no_prepass(pkg, oracle, dim, prec, n, 
     want = pkg.brute_force_cuda_simulate(b, 1e-5, 3, prec, options={"symmetric": 0})
     scale = np.abs(want[:, :2 * dim]).max()
     assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= (2e-6 if prec == 32 else 1e-12) * scale
+
+
+@pytest.mark.parametrize("dim,n", [(3, 20000), (2, 13001), (3, 70001)])
+@pytest.mark.parametrize("prec", [64, 32])
+def test_equal_mass_flavour_matches_the_general_kernels(pkg, oracle, dim, n, prec):
+    """Equal-mass systems (e.g. the Plummer config) run the pair kernels without the masses -- 13 instead of 15 packed
+    instructions per two pairs -- with the common mass applied once per body and the padding bodies parked out of
+    range.  Forces against the oracle and against the general kernels (option equal_mass=0), a few fused steps, and a
+    set where only ONE body differs in mass (must fall back by itself)."""
+    gen = pkg.generators
+    b = gen.uniform_cube(n, dim, seed=900 + n)
+    b[:, 2 * dim] = b[0, 2 * dim]                         # every body the same mass
+    b[17, :dim] = b[3, :dim]
+    b[101, :dim] = b[100, :dim] + 2e-6
+    if prec == 32:
+        b = gen.round_to_float(b)
+    with pkg.NBodyCuda(dim, n, prec) as ctx:
+        ctx.upload(b)
+        f = ctx.forces()
+        assert "[equal-mass chains]" in ctx.plan, ctx.plan
+        ctx.step(1e-5, 3)
+        got = b.copy()
+        ctx.download(got)
+    with pkg.NBodyCuda(dim, n, prec) as ctx:
+        ctx.set_option("equal_mass", 0)
+        ctx.upload(b)
+        f0 = ctx.forces()
+        assert "[equal-mass chains]" not in ctx.plan
+        ctx.step(1e-5, 3)
+        want = b.copy()
+        ctx.download(want)
+    if prec == 64:
+        idx = np.arange(0, n, max(1, n // 2000))
+        assert rel(pkg, f[idx], oracle.forces_targets(b, idx)).max() <= TOL64
+        assert rel(pkg, f, f0).max() <= 2e-12
+    else:
+        idx = np.arange(0, n, max(1, n // 2000))
+        e = rel(pkg, f[idx], oracle.forces_targets(b, idx))
+        assert np.all(e <= pkg.fp32_error_bound(oracle.condition_targets(b, idx)))
+        assert np.percentile(rel(pkg, f, f0), 99) <= 1e-5
+    scale = np.abs(want[:, :2 * dim]).max()
+    assert np.abs(got[:, :2 * dim] - want[:, :2 * dim]).max() <= (2e-6 if prec == 32 else 1e-12) * scale
+    b2 = b.copy()
+    b2[n // 2, 2 * dim] *= 2.0
+    with pkg.NBodyCuda(dim, n, prec) as ctx:
+        ctx.upload(b2)
+        ctx.forces()
+        assert "[equal-mass chains]" not in ctx.plan
 
 
 # ------------------------------------------------------------------ -a 1 column and validation print on the device
