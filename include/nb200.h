@@ -212,24 +212,38 @@ int nb200_last_elapsed_ms(const nb200_ctx* ctx, double* ms);
 /* Kernel launches issued by this context since creation (our own kernels only). */
 long long nb200_launch_count(const nb200_ctx* ctx);
 
-/* Tuning knobs (all optional; 0 restores the heuristic):
- *   "variant"     index into the compiled (targets/thread, j-split, block) table, -1 = auto
- *   "seg_tiles"   source tiles (of 256 bodies) per work unit
- *   "grid_mult"   persistent CTAs = grid_mult * (SMs * occupancy) / 16  (16 = exactly resident)
- *   "overlap"     1 = own source rows first (fused exchange: one launch, the peer handshake is taken
- *                 when a CTA first needs remote rows; NCCL: local pass | all-gather | remote pass),
- *                 0 = one pass over all sources after the handshake / all-gather, -1 = auto (default:
- *                 1 with the fused exchange, 0 with NCCL)
+/* Options (all optional; the defaults are the measured choices):
+ *   "deterministic" 1 = bit-reproducible sums: the ordered pass writes its unit partial sums to per-segment slots and adds
+ *                 them in segment order instead of meeting in FP64 atomics.  Identical bits from run to run AND between
+ *                 1 and N GPUs / shards (every target's sum is the same expression on any shard count).  Costs the
+ *                 pair-symmetric pass (2.8 instead of 3.7 T interactions/s at N = 2^20).  Default 0.
+ *   "equal_mass"  0 = never use the equal-mass flavour of the pair kernels (default: used when every body has the same
+ *                 mass); set before the upload
+ *   "symmetric"   1/0 = pair-symmetric pass on/off (default: on from 12288 bodies): every unordered pair is evaluated once
+ *                 and feeds both bodies, like the j > i loop of brute_force_seq_n_body (methods.cpp:18-39); across ranks the
+ *                 reaction sums are pushed to their owner over NVLink (needs the fused exchange)
+ *   "detect"      1/0 = close-pair pre-pass (hash grid) on/off (default: on from 49152 bodies); without it the
+ *                 pair-symmetric pass applies the exact cut-off to every pair, the ordered pass tracks the minimum r^2
+ *   "sym_algo"    how the pair-symmetric kernel sums the reactions on the streamed sources: 0 shared-memory transpose,
+ *                 1 register rotation through the warp, 2 (FP32 default) rotation with decoupled hand-over
+ *   "sym_ti", "sym_block"  register-block shape of the pair-symmetric kernel: targets per thread x threads per CTA.
+ *                 FP32: 8 x 128 (default), 4 x 256, 4 x 128 (default up to 24576 bodies per shard); FP64: 4 x 256, 2 x 256, 2 x 128
+ *   "seg_tiles" / "seg_sub"  source tiles / sub-tiles (128 sources FP32, 64 FP64) per work unit
+ *   "variant"     index into the compiled (targets/thread, j-split, block) table of the ordered pass, -1 = auto
+ *   "grid_mult"   ordered pass: persistent CTAs = grid_mult * (SMs * occupancy) / 16  (16 = exactly resident)
  *   "exchange"    1 = fused NVLink peer stores from the epilogue (default when attached), 0 = ncclAllGather
+ *   "overlap"     ordered pass on several GPUs: 1 = own source rows first (the peer handshake is taken when a CTA first needs
+ *                 remote rows; NCCL: local pass | all-gather | remote pass), 0 = one pass after the handshake, -1 = auto
+ *   "shard_upload" 1 (default with the fused exchange) = nb200_upload_aos copies only the rows a shard owns and stores
+ *                 their packed source rows into every peer's buffers (the call is then collective over the ranks), 0 = every
+ *                 rank uploads and packs all n bodies
+ *   "pdl"         0 = no programmatic dependent launch between the pair-symmetric pass and its finish kernel (default on)
+ *   "spin_timeout_ms"  bound of every device-side wait on a peer's flag (default 30000): when it expires the call returns
+ *                 NB200_ESTATE naming the peer and what was awaited, and the context refuses further work
  *   "trace"       1 = append a CUDA-event timeline of shard 0 to nb200_plan() after nb200_step
- *   "symmetric"   1/0 = pair-symmetric pass on/off (default on whenever the close-pair pre-pass runs):
- *                 every unordered pair is evaluated once and feeds both bodies, like the j > i loop of
- *                 brute_force_seq_n_body (methods.cpp:18-39); across ranks the reaction sums are pushed
- *                 to their owner over NVLink (needs the fused exchange)
- *   "sym_ti"      4 | 8 targets per thread in the FP32 pair-symmetric kernel (0 = auto)
- *   "sym_itile"   256 | 1024 targets per i-tile of the pair-symmetric pass (0 = auto = 1024; 256 is an
- *                 experiment for small N on one shard that did not pay off, kept for measurements)
- * Returns NB200_EINVAL for an unknown key. */
+ *   "sym_itile"   256 = one-source-tile i-tiles (4 x 64 threads, transpose flavour): a small-N experiment kept for measurements
+ *   "debug_fake_peer"  test hook for the time-out path on one GPU (a detached shard waits for a peer that does not exist)
+ * All ranks of a sharded run must set the same options.  Returns NB200_EINVAL for an unknown key. */
 int nb200_set_option(nb200_ctx* ctx, const char* key, long value);
 
 /* Human-readable one-line description of the launch plan of the last call (for logs). */

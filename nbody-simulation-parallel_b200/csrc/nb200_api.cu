@@ -178,6 +178,8 @@ struct Shard {
     void* peer_src[2][NB_MAX_PEERS] = {{nullptr}};    // peers' source buffers, mapped into this device
     unsigned long long* peer_flags[NB_MAX_PEERS] = {nullptr};
     bool ipc_opened = false;                          // peer pointers came from cudaIpcOpenMemHandle
+    double* det_slots = nullptr;                      // "deterministic" option: [segments][3][tpad] unit partial sums
+    size_t det_slots_doubles = 0;
     unsigned long long* err_host = nullptr;           // page-locked, device-mapped: what a timed-out flag wait was waiting for
     unsigned long long* err_dev = nullptr;            // its device address
 };
@@ -228,7 +230,7 @@ struct nb200_ctx {
     double common_mass = 0.0;
     bool dead = false;            // a peer handshake timed out: the ranks' step counters may have diverged
     // options
-    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0, opt_seg_sub = 0, opt_shard_upload = -1, opt_pdl = -1, opt_eqm = -1;
+    int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0, opt_seg_sub = 0, opt_shard_upload = -1, opt_pdl = -1, opt_eqm = -1, opt_deterministic = 0;
     long opt_spin_timeout_ms = 30000;   // bound of every device-side wait on a peer's flag
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
@@ -424,6 +426,7 @@ void free_shard(Shard& s) {
     }
     cudaFree(s.flags);
     if (s.err_host) cudaFreeHost(s.err_host);
+    cudaFree(s.det_slots);
     cudaFree(s.grid_keys); cudaFree(s.grid_counts); cudaFree(s.suspect); cudaFree(s.sym_rows); cudaFree(s.sym_prefix); cudaFree(s.gacc); cudaFree(s.sym_done);
     for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
     cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
@@ -502,7 +505,10 @@ int make_plan(nb200_ctx* ctx, const Shard& s, Plan* out) {
     const long long span = ctx->tiles_per_shard * NB_TILE;   // targets incl. tile padding
     int v = ctx->opt_variant;
     int grid = 0;
-    if (v < 0 || v >= kNumVariants) {
+    if (ctx->opt_deterministic) {
+        // one shape and one segmentation for every shard count: each target's sum is the same expression on 1 and on N GPUs
+        v = (v >= 0 && v < kNumVariants) ? v : 0;
+    } else if (v < 0 || v >= kNumVariants) {
         // largest i-tile that still gives every resident CTA >= 8 units at >= 8 tiles per unit,
         // else the smallest i-tile
         v = kNumAutoVariants - 1;
@@ -519,6 +525,7 @@ int make_plan(nb200_ctx* ctx, const Shard& s, Plan* out) {
     const int itile = kVariants[v].itile();
     const int nit = (int)((span + itile - 1) / itile);
     int seg = ctx->opt_seg_tiles;
+    if (seg <= 0 && ctx->opt_deterministic) seg = 16;
     if (seg <= 0) {
         // aim for ~64 units per resident CTA, at least 8 tiles per unit when the problem allows
         const long long want_units = 64LL * grid;
@@ -688,6 +695,18 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
     P.lazy_wait = hs.lazy ? 1 : 0;
     P.units_per_itile = units_per_itile;
     if (nseg_total == 0) return NB200_OK;
+    if (ctx->opt_deterministic) {
+        const size_t need = (size_t)nseg_total * 3 * s.tpad;
+        if (s.det_slots_doubles < need) {
+            CK(cudaStreamSynchronize(s.compute));
+            if (s.det_slots) CK(cudaFree(s.det_slots));
+            s.det_slots = nullptr;
+            CK(cudaMalloc(&s.det_slots, need * sizeof(double)));
+            s.det_slots_doubles = need;
+        }
+        P.slots = s.det_slots;
+        P.nseg_total = nseg_total;
+    }
     const Variant& V = kVariants[pl.variant];
     ForceKernel k = pick_kernel(ctx->dim, ctx->f64, pl.variant, pl.flags);
     const int units = pl.n_itiles * nseg_total;
@@ -706,7 +725,7 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
 // pair, ~10 % slower than the plain chains, but 7.5 instead of 11 FMA-pipe lane-ops per interaction and no extra launches)
 constexpr size_t kSymMinN = 12288;
 bool use_symmetric(const nb200_ctx* ctx, bool stepping) {
-    if (ctx->opt_symmetric == 0) return false;
+    if (ctx->opt_symmetric == 0 || ctx->opt_deterministic) return false;
     if (ctx->opt_symmetric < 0 && !use_detect(ctx) && ctx->n < kSymMinN) return false;
     if (ctx->opt_symmetric > 0 && !use_detect(ctx) && ctx->opt_detect != 0 && ctx->n < kSymMinN) return false;   // explicit 1 keeps meaning "when the pre-pass runs" below the threshold
     if (ctx->world == 1) return true;
@@ -1460,6 +1479,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
             return fail(ctx, NB200_ESTATE, "set 'equal_mass' before the upload (it decides where the padding bodies go)");
         ctx->opt_eqm = value < 0 ? -1 : (value != 0);
     }
+    else if (!strcmp(key, "deterministic")) ctx->opt_deterministic = value != 0;
     else if (!strcmp(key, "pdl")) ctx->opt_pdl = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "shard_upload")) ctx->opt_shard_upload = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);
@@ -1654,7 +1674,7 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
     // peer-store exchange it lets a rank start on its own sources before its peers finish.
     // auto: own-rows-first for the fused exchange and for detached shards; no split around NCCL (its
     // kernels spin on SMs next to our persistent CTAs -- measured slower than exposing the gather)
-    const bool split = ctx->world > 1 && (ctx->opt_overlap < 0 ? !use_nccl : ctx->opt_overlap != 0);
+    const bool split = ctx->world > 1 && !ctx->opt_deterministic && (ctx->opt_overlap < 0 ? !use_nccl : ctx->opt_overlap != 0);
     if (use_nccl) { if (int rcn = ensure_nccl_single_process(ctx)) return rcn; }
     NcclApi* nccl = use_nccl ? nccl_api() : nullptr;
     if (use_nccl && !ctx->shards[0].comm_nccl) return fail(ctx, NB200_ESTATE, "no exchange attached (NCCL or peer stores)");

@@ -62,6 +62,11 @@ struct NbForceParams {
     // diverged peer costs an error return (NB200_ESTATE), not a hung GPU
     unsigned long long* err_word;
     unsigned long long spin_timeout_ns;
+    // "deterministic" option: instead of meeting in FP64 atomics (whose order varies from run to run) the unit partial
+    // sums go to slots[segment][3][tpad] and the epilogue adds them in segment order: bit-identical results from run to
+    // run and, with the segments cut on global tile boundaries, between 1 and N GPUs
+    double* slots;
+    int nseg_total;
 };
 
 // what a timed-out wait records: kind << 56 | peer rank << 48 | awaited value (low 48 bits)

@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
                 for (int o = JS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (part == 0) {
                     const int li = it * ITILE + group + t * GROUPS;
-                    atomicAdd(&P.acc[(size_t)d * P.tpad + li], v);
+                    if (P.slots) __stcg(&P.slots[((size_t)seg * 3 + d) * P.tpad + li], v);
+                    else atomicAdd(&P.acc[(size_t)d * P.tpad + li], v);
                 }
             }
         __threadfence();
@@ -337,9 +338,15 @@ __global__ void __launch_bounds__(BLOCK) nb_force_kernel(const NbForceParams P) 
                 double S[3];
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                    double* ap = &P.acc[(size_t)d * P.tpad + li];
-                    S[d] = __ldcg(ap) * P.acc_scale;
-                    __stcg(ap, 0.0);                       // self-clean for the next step
+                    if (P.slots) {
+                        double v = 0.0;                    // fixed order: segment 0, 1, 2, ...
+                        for (int sg = 0; sg < P.nseg_total; ++sg) v += __ldcg(&P.slots[((size_t)sg * 3 + d) * P.tpad + li]);
+                        S[d] = v * P.acc_scale;
+                    } else {
+                        double* ap = &P.acc[(size_t)d * P.tpad + li];
+                        S[d] = __ldcg(ap) * P.acc_scale;
+                        __stcg(ap, 0.0);                   // self-clean for the next step
+                    }
                 }
                 if (li >= P.n_local) continue;
                 const double m = P.mass[li];

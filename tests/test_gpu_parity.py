@@ -410,6 +410,42 @@ def test_detached_shards_cover_all_targets(pkg, oracle, world, prec):
     assert np.abs(stepped[:, :3] - want[:, :3]).max() <= xt
 
 
+@pytest.mark.parametrize("prec", [64, 32])
+@pytest.mark.parametrize("dim,n", [(3, 9000), (2, 20011)])
+def test_deterministic_option_is_bitwise_reproducible_across_shard_counts(pkg, oracle, dim, n, prec):
+    """Option deterministic=1: unit partial sums go to per-segment slots and are added in segment order instead of
+    meeting in FP64 atomics.  Two runs give identical bits, and so do 1, 2, 3 and 8 target shards (virtual ranks on one
+    GPU: the sharded pass of every rank), because every target's sum is the same expression on any shard count
+    ("1 vs 2/4/8 GPUs must be bit-identical")."""
+    b = pkg.generators.uniform_cube(n, dim, seed=4242 + n)
+    b[17, :dim] = b[3, :dim]
+    if prec == 32:
+        b = pkg.generators.round_to_float(b)
+    opts = {"deterministic": 1}
+    f1 = pkg.brute_force_cuda_n_body(b, prec, options=opts)
+    f1b = pkg.brute_force_cuda_n_body(b, prec, options=opts)
+    assert np.array_equal(f1, f1b)
+    if prec == 64:
+        assert rel(pkg, f1, oracle.forces(b)).max() <= TOL64
+    else:
+        assert_fp32_parity(pkg, oracle, f1, b, "deterministic")
+    a1 = pkg.brute_force_cuda_simulate(b, 1e-4, 2, prec, options=opts)
+    for world in (2, 3, 8):
+        forces = np.zeros((n, dim))
+        stepped = b.copy()
+        for r in range(world):
+            with pkg.NBodyCuda(dim, n, prec, rank=r, world=world, device=0) as ctx:
+                ctx.set_option("deterministic", 1)
+                ctx.upload(b)
+                ctx.forces(out=forces)
+                ctx.step(1e-4, 1)
+                ctx.download(stepped)
+        assert np.array_equal(forces, f1), f"world={world}: forces differ in {np.count_nonzero(forces != f1)} components"
+        one = pkg.brute_force_cuda_simulate(b, 1e-4, 1, prec, options=opts)
+        assert np.array_equal(stepped, one), f"world={world}: one step differs"
+    assert np.all(np.isfinite(a1))
+
+
 def test_error_paths(pkg):
     with pytest.raises(pkg.NB200Error):
         pkg.NBodyCuda(4, 10)                         # dim must be 2 or 3 (main.cpp:889-892)
@@ -500,6 +536,10 @@ def test_single_process_multi_gpu_matches_one_gpu(pkg, ngpus, prec):
                                            options={"detect": 1, "symmetric": 1, "sym_ti": ti, "seg_tiles": 3})
         err = np.abs(ag - a1).max() / np.abs(a1).max()
         assert err <= tol, f"cross-rank symmetric TI={ti}: {err:.3e}"
+    # deterministic option: identical bits on 1 and on N GPUs, forces and trajectory
+    d1 = pkg.brute_force_cuda_simulate(b, 1e-3, 5, prec, options={"deterministic": 1})
+    dg = pkg.brute_force_cuda_simulate(b, 1e-3, 5, prec, ngpus=ngpus, options={"deterministic": 1})
+    assert np.array_equal(dg, d1), f"deterministic: {np.count_nonzero(dg != d1)} state components differ between 1 and {ngpus} GPUs"
     # shard-local upload (default: every shard takes only its own rows from the caller's array and stores their source
     # rows into all shards' buffers) against the full upload on every shard: identical state, identical trajectories
     for b_up in (b, pkg.generators.reference_range(n, 3, seed=3)):
