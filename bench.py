@@ -32,10 +32,8 @@ import time
 
 import numpy as np
 
-# rank 0 prints exactly ONE JSON line on stdout.  Without a caller-set NCCL_DEBUG keep NCCL quiet; a caller that
-# asks for INFO (the driver's communicator check) gets it untouched.
-os.environ.setdefault("NCCL_DEBUG", "WARN")
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # banner and communicator lines go to stderr, never into the JSON line
+# rank 0 prints exactly ONE JSON line on stdout.  NCCL_DEBUG is left entirely to the caller: unset, NCCL prints nothing
+# (not even its version banner); a caller that asks for INFO (the driver's communicator check) gets it untouched.
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
