@@ -46,22 +46,10 @@ struct NbSymRow {
 // sub-tiles per source tile a symmetric row's units are measured in
 __host__ __device__ constexpr int nb_sym_subtiles(bool f64, int algo) { return algo == 0 ? 1 : f64 ? 4 : 2; }
 
-// compile-time experiments of the rotation flavour (csrc/Makefile EXTRA=-D...)
-#ifndef NB_ROT_UNROLL
-#define NB_ROT_UNROLL 1
-#endif
-#ifndef NB_ROT_SHFL_ASM
-#define NB_ROT_SHFL_ASM 1     // in-place shfl.sync: 3675 vs 3534 G inter/s at N = 2^20 (no MOVs at the loop end)
-#endif
-#ifndef NB_ROT_ORDER
-#define NB_ROT_ORDER 0
-#endif
-#ifndef NB_ROT_PIPE
-#define NB_ROT_PIPE 0         // 1: source pairs loaded half a step ahead of their use (LDS.64, no extra registers)
-#endif
-#ifndef NB_ROT_SMEM_ACC
-#define NB_ROT_SMEM_ACC 1     // FP64 per-target sums in shared memory: 3810 vs 3675 (24 registers back for the chains)
-#endif
+// Measured and rejected variants of the rotation flavour (profiles/r02/sym_variants_*.jsonl, small_n.md): step loop
+// unrolled twice (-4 %), source pairs loaded half a step ahead (-8 %: loop-carried loads turn into MOVs), the accumulate
+// FFMA2 ordered for operand reuse in the source (ptxas reschedules them: no effect), __shfl_sync instead of the
+// in-place shfl.sync below (-4 %: 14 MOVs per step), FP64 per-target sums in registers instead of shared memory (-4 %).
 
 struct NbSymParams {
     const void* src;             // tile-planar sources (current step), all bodies (float or double)
@@ -264,11 +252,11 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
                                                     const float (&mi)[TI],
                                                     float2 (&a)[TI][3], float* __restrict__ wout, int lane,
                                                     int hf_begin, int hf_end) {
-    // plane p of the stage as float2: source pair (group g, half h) sits at p * (NB_TILE / 2) + 2 g + h
-    const float2* sx = reinterpret_cast<const float2*>(stage);
-    const float2* sy = sx + NB_TILE / 2;
-    const float2* sz = sy + NB_TILE / 2;                      // D == 3 only
-    const float2* sm = sx + D * (NB_TILE / 2);
+    // plane p of the stage as float4: home group g of half tile hf sits at p * (NB_TILE / 4) + 32 hf + g
+    const float4* sx = reinterpret_cast<const float4*>(stage);
+    const float4* sy = sx + NB_TILE / 4;
+    const float4* sz = sy + NB_TILE / 4;                      // D == 3 only
+    const float4* sm = sx + D * (NB_TILE / 4);
 #pragma unroll
     for (int t = 0; t < TI; ++t)
 #pragma unroll
@@ -299,17 +287,6 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
             const float2 w = __fmul2_rn(inv, inv);
             const float2 s = EQM ? w : __fmul2_rn(w, ms);
             const float2 u = EQM ? w : __fmul2_rn(w, make_float2(mi[t], mi[t]));
-#if NB_ROT_ORDER == 1
-            // s shared by the first three, u by the last three, dz by the middle two (operand reuse cache)
-            a[t][0] = __ffma2_rn(dx, s, a[t][0]);
-            a[t][1] = __ffma2_rn(dy, s, a[t][1]);
-            if (D == 3) {
-                a[t][2] = __ffma2_rn(dz, s, a[t][2]);
-                b[2] = __ffma2_rn(dz, u, b[2]);
-            }
-            b[1] = __ffma2_rn(dy, u, b[1]);
-            b[0] = __ffma2_rn(dx, u, b[0]);
-#else
             a[t][0] = __ffma2_rn(dx, s, a[t][0]);
             b[0] = __ffma2_rn(dx, u, b[0]);
             a[t][1] = __ffma2_rn(dy, s, a[t][1]);
@@ -318,7 +295,6 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
                 a[t][2] = __ffma2_rn(dz, s, a[t][2]);
                 b[2] = __ffma2_rn(dz, u, b[2]);
             }
-#endif
         }
     };
     // this pair of sources is done for this lane: pass its sums on to lane l - 1
@@ -326,15 +302,10 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             float2 v = DECOUPLE ? __fadd2_rn(trav[d], b[d]) : b[d];
-#if NB_ROT_SHFL_ASM
             // in-place shuffles: the loop-carried pair keeps its registers (no MOVs at the loop end)
             asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+f"(v.x) : "r"(from));
             asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+f"(v.y) : "r"(from));
             trav[d] = v;
-#else
-            trav[d].x = __shfl_sync(0xffffffffu, v.x, from);
-            trav[d].y = __shfl_sync(0xffffffffu, v.y, from);
-#endif
         }
     };
     const float2 zero2 = make_float2(0.f, 0.f);
@@ -346,42 +317,12 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int d = 0; d < 3; ++d) trav[h][d] = zero2;
-#if NB_ROT_PIPE
-        // loads half a step ahead of their use: the first pair of the NEXT group is fetched while the second
-        // pair of this group is worked on, the second pair of this group while the first pair is
-        int g = hf * 64 + 2 * lane;
-        float2 Ax = sx[g], Ay = sy[g], Am = sm[g], Az = zero2;
-        if (D == 3) Az = sz[g];
-#endif
-        NB_UNROLL(NB_ROT_UNROLL)
+#pragma unroll 1
         for (int k = 0; k < 32; ++k) {
-#if NB_ROT_PIPE
-            const float2 Bx = sx[g + 1], By = sy[g + 1], Bm = sm[g + 1];
-            float2 Bz = zero2;
-            if (D == 3) Bz = sz[g + 1];
-            g = hf * 64 + 2 * ((lane + k + 1) & 31);
-            {
-                float2 b[3];
-#pragma unroll
-                for (int d = 0; d < 3; ++d) b[d] = DECOUPLE ? zero2 : trav[0][d];
-                chains(Ax, Ay, Az, Am, b);
-                hand_over(trav[0], b);
-            }
-            Ax = sx[g]; Ay = sy[g]; Am = sm[g];
-            if (D == 3) Az = sz[g];
-            {
-                float2 b[3];
-#pragma unroll
-                for (int d = 0; d < 3; ++d) b[d] = DECOUPLE ? zero2 : trav[1][d];
-                chains(Bx, By, Bz, Bm, b);
-                hand_over(trav[1], b);
-            }
-#else
             const int q = hf * 32 + ((lane + k) & 31);
-            const float4 X = reinterpret_cast<const float4*>(sx)[q], Y = reinterpret_cast<const float4*>(sy)[q],
-                         M = reinterpret_cast<const float4*>(sm)[q];
+            const float4 X = sx[q], Y = sy[q], M = sm[q];
             float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (D == 3) Z = reinterpret_cast<const float4*>(sz)[q];
+            if (D == 3) Z = sz[q];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const float2 xs = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
@@ -394,7 +335,6 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
                 chains(xs, ys, zs, ms, b);
                 hand_over(trav[h], b);
             }
-#endif
         }
         // after 32 hand-overs the sums of home group `lane` are complete and back in lane `lane`
         float4* wo = reinterpret_cast<float4*>(wout + hf * 128 + 4 * lane);
@@ -673,9 +613,9 @@ nb_force_sym_kernel(const NbSymParams P) {
             if (P.suspect) suspect |= P.suspect[it * ITILE + tid + t * BLOCK] != 0;
         }
         const bool warp_suspect = !P.suspect || __any_sync(0xffffffffu, suspect) != 0;
-        // FP64 sums of the own targets over the unit: in registers, or (rotation flavours, experiment) in the
-        // shared memory the transpose scratch no longer needs -- 24 registers back for the chains
-        constexpr bool SACC = NB_ROT_SMEM_ACC && !F64 && ALGO != 0;
+        // FP64 sums of the own targets over the unit: in registers, or (FP32 rotation flavours) in the shared memory
+        // the transpose scratch no longer needs -- 24 registers back for the chains
+        constexpr bool SACC = !F64 && ALGO != 0;
         double* sacc = reinterpret_cast<double*>(scr_all) + tid;     // [TI * 3][BLOCK]
         double accd[SACC ? 1 : TI][3];
         if constexpr (SACC) {
@@ -712,7 +652,7 @@ nb_force_sym_kernel(const NbSymParams P) {
                 for (int tt = 0; tt < TI; ++tt) exact_tile |= (ts + t == own_tile[tt]);
             }
             if constexpr (F64) {
-                static_assert(!SACC, "smem accumulators are an FP32 experiment");
+                static_assert(!SACC, "shared-memory accumulators belong to the FP32 rotation flavours");
                 const double* dstage = reinterpret_cast<const double*>(stage);
                 const double(&pos)[TI][3] = reinterpret_cast<const double(&)[TI][3]>(tq);
                 const double(&mid)[TI] = reinterpret_cast<const double(&)[TI]>(mi);
