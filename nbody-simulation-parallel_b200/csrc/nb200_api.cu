@@ -367,8 +367,9 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
         unsigned cap = 1024;
         while ((long long)cap < 2 * ctx->ntiles * NB_TILE) cap <<= 1;
         s.grid_cap = cap;
-        CK(cudaMalloc(&s.grid_keys, (size_t)cap * sizeof(unsigned long long)));
-        CK(cudaMalloc(&s.grid_counts, (size_t)cap * sizeof(unsigned)));
+        // keys and counts in one allocation: one memset per step clears both
+        CK(cudaMalloc(&s.grid_keys, (size_t)cap * (sizeof(unsigned long long) + sizeof(unsigned))));
+        s.grid_counts = reinterpret_cast<unsigned*>(s.grid_keys + cap);
         CK(cudaMalloc(&s.suspect, tp));
         CK(cudaMemset(s.suspect, 1, tp));
         {
@@ -427,7 +428,7 @@ void free_shard(Shard& s) {
     cudaFree(s.flags);
     if (s.err_host) cudaFreeHost(s.err_host);
     cudaFree(s.det_slots);
-    cudaFree(s.grid_keys); cudaFree(s.grid_counts); cudaFree(s.suspect); cudaFree(s.sym_rows); cudaFree(s.sym_prefix); cudaFree(s.gacc); cudaFree(s.sym_done);
+    cudaFree(s.grid_keys); cudaFree(s.suspect); cudaFree(s.sym_rows); cudaFree(s.sym_prefix); cudaFree(s.gacc); cudaFree(s.sym_done);
     for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
     cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
     cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.bounds); cudaFree(s.cmp); cudaFree(s.tile_done); cudaFree(s.sched);
@@ -550,6 +551,24 @@ struct Ranges {
 
 int nsegs(int b, int e, int seg) { return e > b ? (e - b + seg - 1) / seg : 0; }
 
+// Launch with programmatic dependent launch allowed: the kernel may start (and run its prologue) while its predecessor in
+// the stream drains; it waits for the predecessor itself (nb_grid_dep_wait).  A step of a small problem is two short
+// launches back to back: the launch latency between them is the part of the step this hides.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // launch one pass of the force kernel on shard s over the given source-tile ranges
 // close-pair pre-pass on the shard's compute stream: hash-grid insert of every source, then the
 // suspect flag of every own (padded) target.  Reads src[cur], so it runs after the peer handshake.
@@ -567,18 +586,18 @@ int launch_detect(nb200_ctx* ctx, Shard& s, double cutoff, int cur) {
     // but keep cell indices far inside the int64 range
     const double h = cs > 0.0 ? sqrt(cs) * 1.001 : ldexp(ctx->xmax * ctx->pos_scale, -40);
     g.inv_h = 1.0 / h;
-    CK(cudaMemsetAsync(s.grid_keys, 0xFF, (size_t)s.grid_cap * sizeof(unsigned long long), s.compute));
-    CK(cudaMemsetAsync(s.grid_counts, 0, (size_t)s.grid_cap * sizeof(unsigned), s.compute));
+    // one memset (keys = empty, counts = -1), then insert -> query -> force pass chained by programmatic dependent launch
+    CK(cudaMemsetAsync(s.grid_keys, 0xFF, (size_t)s.grid_cap * (sizeof(unsigned long long) + sizeof(unsigned)), s.compute));
     const int threads = 256;
     const int bi = (int)((nbodies + threads - 1) / threads), bq = (s.tpad + threads - 1) / threads;
-#define NB_GRID(DD, RR)                                                                                    \
-    nb_grid_insert_kernel<DD, RR><<<bi, threads, 0, s.compute>>>((const RR*)s.src[cur], nbodies, g);       \
-    nb_grid_query_kernel<DD, RR><<<bq, threads, 0, s.compute>>>((const RR*)s.src[cur], s.tgt_base, s.tpad, \
-                                                                 nbodies, g, s.suspect)
+    const bool pdl = ctx->opt_pdl != 0;
+#define NB_GRID(DD, RR)                                                                                                      \
+    CK(launch_pdl(nb_grid_insert_kernel<DD, RR>, bi, threads, 0, s.compute, false, (const RR*)s.src[cur], nbodies, g));      \
+    CK(launch_pdl(nb_grid_query_kernel<DD, RR>, bq, threads, 0, s.compute, pdl, (const RR*)s.src[cur], s.tgt_base, s.tpad,   \
+                  nbodies, g, s.suspect))
     if (D == 3) { if (ctx->f64) { NB_GRID(3, double); } else { NB_GRID(3, float); } }
     else        { if (ctx->f64) { NB_GRID(2, double); } else { NB_GRID(2, float); } }
 #undef NB_GRID
-    CK(cudaGetLastError());
     ctx->launches += 2;
     return NB200_OK;
 }
@@ -802,24 +821,6 @@ int build_sym_rows(nb200_ctx* ctx, Shard& s, int seg_sub, int seg_ord, int subt,
     return NB200_OK;
 }
 
-// Launch with programmatic dependent launch allowed: the kernel may start (and run its prologue) while its predecessor in
-// the stream drains; it waits for the predecessor itself (nb_grid_dep_wait).  A step of a small problem is two short
-// launches back to back: the launch latency between them is the part of the step this hides.
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)block);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
 // symmetric force kernel, [push of the reaction sums to their owners], finish kernel (forces or integrate)
 int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff, double dt, int cur, bool with_flags,
                      const Handshake& hs = Handshake()) {
@@ -889,9 +890,9 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     Q.total_units = s.sym_prefix_host.back();
     Q.cutoff = cutoff * ctx->pos_scale * ctx->pos_scale;
     const int grid = std::min(resident, Q.total_units);
-    // one shard, no pre-pass: the step is this pass + the finish kernel, chained by programmatic dependent launch
+    // one shard: [pre-pass insert -> query ->] this pass -> finish kernel are chained by programmatic dependent launch
     const bool pdl = !cross && ctx->world == 1 && ctx->opt_pdl != 0;
-    CK(launch_pdl(kfn, grid, block, smem, s.compute, pdl && !with_flags, Q));
+    CK(launch_pdl(kfn, grid, block, smem, s.compute, pdl, Q));
     ctx->launches++;
 
     NbSymFinish F;

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) nb_energy_kernel(const real* __restrict__
 // lies in adjacent cells, so both of its bodies are flagged; false positives only cost speed.
 struct NbGrid {
     unsigned long long* keys;   // open addressing, linear probing; ~0ull = empty
-    unsigned* counts;
+    unsigned* counts;           // bodies in the cell MINUS ONE: one memset of 0xFF clears keys and counts together
     unsigned mask;              // capacity - 1 (power of two)
     double inv_h;               // 1 / cell edge, in source units
 };
@@ -275,6 +275,7 @@ __global__ void nb_grid_insert_kernel(const real* __restrict__ src, long long nb
     // nbodies: every source incl. the zero-mass padding that sits on a real body's position; with parked padding
     // (equal-mass systems) only the real bodies
     constexpr int NP = D + 1;
+    nb_launch_dependents();     // the query kernel may queue up behind this one (it waits for its completion itself)
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbodies) return;
     const real* tb = src + (size_t)(b / NB_TILE) * (NB_TILE * NP) + (b % NB_TILE);
@@ -295,6 +296,8 @@ template <int D, typename real>
 __global__ void nb_grid_query_kernel(const real* __restrict__ src, long long tgt_base, int tpad,
                                      long long nbodies, NbGrid g, unsigned char* __restrict__ suspect) {
     constexpr int NP = D + 1;
+    nb_grid_dep_wait();         // every insert is complete and visible
+    nb_launch_dependents();     // the force pass may queue up
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= tpad) return;
     const long long b = tgt_base + li;
@@ -311,7 +314,7 @@ __global__ void nb_grid_query_kernel(const real* __restrict__ src, long long tgt
                 unsigned slot = nb_slot_of(key, g.mask);
                 for (;;) {
                     const unsigned long long k = g.keys[slot];
-                    if (k == key) { total += g.counts[slot]; break; }
+                    if (k == key) { total += g.counts[slot] + 1u; break; }
                     if (k == ~0ull) break;
                     slot = (slot + 1) & g.mask;
                 }
