@@ -169,6 +169,8 @@ struct Shard {
     std::vector<NbSymRow> sym_rows_host;
     std::vector<int> sym_prefix_host;
     int sym_key_seg = 0, sym_key_world = 0, sym_key_tpi = 0;
+    const void* occ_fn = nullptr;        // pair-symmetric kernel of the last occupancy query and its answer
+    int occ_blocks = 0;
     double* gacc = nullptr;                           // [3][nalloc]
     unsigned* sym_done = nullptr;                     // [2] push / finish CTA counters
     // fused NVLink exchange (peer stores from the epilogue + flag handshake)
@@ -199,7 +201,7 @@ constexpr size_t kSymSmallN = 0;
 // with 4 x 256 threads, 3864 with 8 x 128 and rotation (profiles/r02_sym_variants.jsonl).
 constexpr int kSymAlgoDefault = 2;     // FP64 has no flavour 2: it takes 1
 constexpr int kSymTiF32 = 8;
-constexpr int kSymTiF64 = 4;
+constexpr int kSymTiF64 = 8;     // 8 x 128 on two CTAs per SM: 1707 vs 1584 G inter/s (4 x 256) at N = 2^20, 3D
 
 }  // namespace
 
@@ -279,6 +281,10 @@ template <int D, bool F64, int ALGO> SymKernel sym_kernel_of(SymShape sh) {
     if (sh.block == 64) return nb_force_sym_kernel<D, F64, 4, 64, 0>;            // small-N experiment, transpose only
     if constexpr (F64) {
         if (sh.ti == 2) return sh.block == 128 ? nb_force_sym_kernel<D, true, 2, 128, ALGO> : nb_force_sym_kernel<D, true, 2, 256, ALGO>;
+        if constexpr (ALGO == 1) {
+            if (sh.ti == 8) return nb_force_sym_kernel<D, true, 8, 128, 1>;
+            if (sh.block == 128) return nb_force_sym_kernel<D, true, 4, 128, 1>;
+        }
         return nb_force_sym_kernel<D, true, 4, 256, ALGO>;
     } else {
         if (sh.ti == 8) return nb_force_sym_kernel<D, false, 8, 128, ALGO>;
@@ -294,11 +300,11 @@ template <int D, bool F64> SymKernel sym_kernel_of(SymShape sh, int algo) {
 // rotation; FP64: 4 x 256 with the rotation); every other combination runs the general kernels, which are correct for
 // equal masses too.
 bool sym_has_eqm(bool f64, SymShape sh, int algo) {
-    if (f64) return algo == 1 && sh.ti == 4 && sh.block == 256;
+    if (f64) return algo == 1 && ((sh.ti == 4 && sh.block == 256) || (sh.ti == 8 && sh.block == 128));
     return algo == 2 && sh.block == 128 && (sh.ti == 8 || sh.ti == 4);
 }
 template <int D> SymKernel sym_kernel_eqm(bool f64, SymShape sh) {
-    if (f64) return nb_force_sym_kernel<D, true, 4, 256, 1, true>;
+    if (f64) return sh.ti == 8 ? nb_force_sym_kernel<D, true, 8, 128, 1, true> : nb_force_sym_kernel<D, true, 4, 256, 1, true>;
     return sh.ti == 8 ? nb_force_sym_kernel<D, false, 8, 128, 2, true> : nb_force_sym_kernel<D, false, 4, 128, 2, true>;
 }
 SymKernel pick_sym_kernel(int dim, bool f64, SymShape sh, int algo, bool eqm = false) {
@@ -308,7 +314,7 @@ SymKernel pick_sym_kernel(int dim, bool f64, SymShape sh, int algo, bool eqm = f
 }
 // every shape this precision can be launched with (for the one-time shared-memory opt-in)
 const SymShape kSymShapesF32[] = {{4, 256}, {8, 128}, {4, 128}, {4, 64}};
-const SymShape kSymShapesF64[] = {{4, 256}, {2, 256}, {2, 128}, {4, 64}};
+const SymShape kSymShapesF64[] = {{4, 256}, {2, 256}, {2, 128}, {8, 128}, {4, 128}, {4, 64}};
 
 // CUDA loads a kernel's code lazily at its first launch; the reference times ONE call per process
 // (safely_execute, utils.h:87-104), so every kernel a call may launch is loaded when the context is created
@@ -401,15 +407,22 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
             CK(cudaFuncSetAttribute((const void*)pick_kernel(D, ctx->f64, v, fl != 0),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem_bytes(D, ctx->f64)));
-    for (const SymShape& sh : ctx->f64 ? kSymShapesF64 : kSymShapesF32)
-        for (int algo = 0; algo <= (sh.block == 64 ? 0 : ctx->f64 ? 1 : 2); ++algo)
+    const SymShape* shapes = ctx->f64 ? kSymShapesF64 : kSymShapesF32;
+    const size_t n_shapes = ctx->f64 ? sizeof kSymShapesF64 / sizeof(SymShape) : sizeof kSymShapesF32 / sizeof(SymShape);
+    for (size_t k = 0; k < n_shapes; ++k) {
+        const SymShape sh = shapes[k];
+        const bool rot_only = ctx->f64 && sh.block == 128 && sh.ti >= 4;
+        for (int algo = rot_only ? 1 : 0; algo <= (sh.block == 64 ? 0 : ctx->f64 ? 1 : 2); ++algo)
             CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, sh, algo), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo)));
-    for (const SymShape& sh : ctx->f64 ? kSymShapesF64 : kSymShapesF32)
+    }
+    for (size_t k = 0; k < n_shapes; ++k) {
+        const SymShape sh = shapes[k];
         for (int algo = 1; algo <= 2; ++algo)
             if (sym_has_eqm(ctx->f64, sh, algo))
                 CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, sh, algo, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo)));
+    }
     return preload_aux_kernels(ctx);
 }
 
@@ -830,32 +843,42 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     const int tiles = (int)ctx->tiles_per_shard;
     // shape = targets per thread x threads per CTA (i-tile = their product); options "sym_ti", "sym_block"
     //   FP32: 8 x 128 (default: fewest hand-overs per chain), 4 x 256, 4 x 128
-    //   FP64: 4 x 256 (one CTA per SM), 2 x 256 and 2 x 128 (two / four CTAs per SM under 128 registers)
+    //   FP64: 8 x 128 (default: two CTAs per SM at 255 registers, half the hand-overs and loads per pair), 4 x 256
+    //         (one CTA per SM), 4 x 128 (three), 2 x 256 and 2 x 128 (two / four CTAs per SM under 128 registers)
     // opt-in shape for small problems on one shard: i-tiles of ONE source tile (4 targets x 64 threads, many
     // small CTAs); option "sym_itile" = 256 selects it
     const bool small = !cross && (ctx->opt_sym_itile ? ctx->opt_sym_itile == 256 : (kSymSmallN > 0 && ctx->n < kSymSmallN));
     SymShape sh{4, 64};
     if (!small) {
         if (ctx->f64) {
-            sh.ti = ctx->opt_sym_ti == 2 ? 2 : ctx->opt_sym_ti == 4 ? 4 : kSymTiF64;
-            sh.block = (sh.ti == 2 && ctx->opt_sym_block == 128) ? 128 : 256;
+            sh.ti = ctx->opt_sym_ti ? ctx->opt_sym_ti : kSymTiF64;
+            sh.block = sh.ti == 8 ? 128 : ctx->opt_sym_block == 128 ? 128 : 256;
         } else {
             sh.ti = ctx->opt_sym_ti == 8 ? 8 : ctx->opt_sym_ti == 4 ? 4 : kSymTiF32;
             sh.block = sh.ti == 8 ? 128 : ctx->opt_sym_block == 128 ? 128 : 256;
         }
     }
     const int algo = small ? 0 : std::min(ctx->opt_sym_algo >= 0 ? ctx->opt_sym_algo : kSymAlgoDefault, ctx->f64 ? 1 : 2);
+    // FP64: the 8 x 128 and 4 x 128 shapes exist for the rotation only
+    if (!small && ctx->f64 && algo == 0 && sh.ti >= 4) sh = SymShape{4, 256};
     const int subt = nb_sym_subtiles(ctx->f64, algo);
-    // small FP32 problems (measured, profiles/r02/small_n.jsonl): 512-target i-tiles on five CTAs per SM balance better
+    // small FP32 problems (measured, profiles/r02/small_n.jsonl): 512-target i-tiles on four CTAs per SM balance better
     // up to N ~ 24576 (N=16384: 0.108 ms/step vs 0.112 with 8 x 128)
     if (!small && !ctx->f64 && !ctx->opt_sym_ti && !ctx->opt_sym_block && !cross && (long long)tiles * NB_TILE <= 24576)
         sh = SymShape{4, 128};
+    const bool eqm = ctx->equal_mass && sym_has_eqm(ctx->f64, sh, algo);
     int resident = 0;
     {
-        int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)pick_sym_kernel(D, ctx->f64, sh, algo), sh.block,
-                                                         nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo)));
-        resident = std::max(1, nb) * s.sms;
+        // asked once per kernel, not once per step: the query is a driver call of several microseconds (more once other
+        // lazily loaded modules live in the context), and a 0.1 ms step has no host time to spare
+        const void* fn = (const void*)pick_sym_kernel(D, ctx->f64, sh, algo, eqm);
+        if (s.occ_fn != fn) {
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, sh.block, nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo)));
+            s.occ_fn = fn;
+            s.occ_blocks = std::max(1, nb);
+        }
+        resident = s.occ_blocks * s.sms;
     }
     // work units: ~18 per resident CTA keep the tail short without paying a unit's fixed cost (target loads, first TMA
     // wait, the FP64 atomics of the target sums) too often; at most 32 tiles, at least one sub-tile
@@ -868,7 +891,6 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     const int ti = sh.ti, block = sh.block;
     const int itile = ti * block;
     const int seg_ord = std::max(1, seg_sub / subt);
-    const bool eqm = ctx->equal_mass && sym_has_eqm(ctx->f64, sh, algo);
     const SymKernel kfn = pick_sym_kernel(D, ctx->f64, sh, algo, eqm);
     const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64, ti, algo);
     if (int rc = build_sym_rows(ctx, s, seg_sub, seg_ord, subt, cross, itile / NB_TILE)) return rc;

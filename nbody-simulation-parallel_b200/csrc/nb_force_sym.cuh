@@ -97,16 +97,26 @@ struct NbSymFinish {
     unsigned* done;              // CTA completion counter for the step signal (self-resetting)
 };
 
-// TMA ring depth of a shape: the 4 x 128 FP32 shape runs five CTAs per SM and has room for two stages only
+// TMA ring depth of a shape: the 4 x 128 FP32 shape was sized for five CTAs per SM (two stages); it runs four now
 // (one tile takes ~10 us to consume, a bulk copy ~1 us to land: two are enough)
 __host__ __device__ constexpr int nb_sym_stages(bool f64, int ti, int block) {
     return ((!f64 && ti == 4 && block == 128) || (f64 && ti == 2)) ? 2 : NB_STAGES;
 }
-// resident CTAs per SM the register allocation is capped for
-__host__ __device__ constexpr int nb_sym_min_blocks(bool f64, int ti, int block) {
+// Resident CTAs per SM the register allocation is capped for.  The 8 x 128 FP32 shape in 3D with per-body masses is
+// compiled for TWO CTAs per SM (245 registers, two warps per scheduler): ptxas keeps more chains in flight per warp and
+// that beats three CTAs at 168 registers by 5 % (3899 vs 3712 G inter/s at N = 2^20, same arithmetic); the shorter 2D
+// and equal-mass chains are faster with three (2D N = 65536: 4627 vs 4423; Plummer N = 262144: 4391 vs 4167).
+// 4 x 128 FP32 (small problems): four CTAs per SM at 128 registers.  Five CTAs at 96 registers are 1 % faster when the
+// library is alone in the process (N = 16384: 0.1002 vs 0.1012 ms/step) but spill 56 bytes per thread, and the cost of
+// that local-memory traffic depends on the rest of the CUDA context: 0.1071 ms once PyTorch has launched one kernel
+// of its own (lazily loaded module), against 0.1016 for this spill-free build (tools/c2_probe.py).
+#ifndef NB_SYM_MB_4X128
+#define NB_SYM_MB_4X128 4
+#endif
+__host__ __device__ constexpr int nb_sym_min_blocks(bool f64, int ti, int block, int dim = 3, bool eqm = false) {
     return block == 64 ? (f64 ? 4 : 7)
-           : f64 ? (ti == 2 ? (block == 256 ? 2 : 4) : 1)
-                 : block == 256 ? 2 : (ti == 8 ? 3 : 5);
+           : f64 ? (ti == 2 ? (block == 256 ? 2 : 4) : ti == 8 ? 2 : block == 128 ? 3 : 1)
+                 : block == 256 ? 2 : (ti == 8 ? ((dim == 3 && !eqm) ? 2 : 3) : NB_SYM_MB_4X128);
 }
 
 static inline size_t nb_sym_smem_bytes(int dim, int block, bool f64, int ti = 0, int algo = 0) {
@@ -503,7 +513,7 @@ __device__ __forceinline__ void nb_tile_f64_sym_rot(const double* __restrict__ s
 
 // ALGO: 0 = shared-memory transpose of the reaction sums, 1 = register rotation, 2 (FP32) = rotation, decoupled
 template <int D, bool F64, int TI, int BLOCK, int ALGO = 0, bool EQM = false>
-__global__ void __launch_bounds__(BLOCK, nb_sym_min_blocks(F64, TI, BLOCK))
+__global__ void __launch_bounds__(BLOCK, nb_sym_min_blocks(F64, TI, BLOCK, D, EQM))
 nb_force_sym_kernel(const NbSymParams P) {
     static_assert(!EQM || ALGO != 0, "the equal-mass flavour exists for the rotation flavours only");
     constexpr int STAGES = nb_sym_stages(F64, TI, BLOCK);

@@ -705,7 +705,8 @@ def test_pair_symmetric_reduction_flavours(pkg, oracle, dim, n, algo, sym_ti, se
 
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("n", [300, 5000, 9473])
-@pytest.mark.parametrize("algo,sym_ti,block,seg_tiles", [(1, 4, 256, 0), (1, 2, 256, 0), (1, 2, 128, 3), (0, 2, 256, 1), (0, 2, 128, 0)])
+@pytest.mark.parametrize("algo,sym_ti,block,seg_tiles", [(1, 8, 128, 0), (1, 8, 128, 3), (1, 4, 256, 0), (1, 4, 128, 0), (1, 2, 256, 0),
+                                                         (1, 2, 128, 3), (0, 2, 256, 1), (0, 2, 128, 0), (0, 4, 256, 0)])
 def test_pair_symmetric_fp64_shapes(pkg, oracle, dim, n, algo, sym_ti, block, seg_tiles):
     """FP64 pair-symmetric kernel: both reaction-sum reductions and all register-block shapes hold the
     1e-12 bound against the oracle (forces, then a few fused steps against the ordered pass)."""
