@@ -227,7 +227,8 @@ long long nb200_launch_count(const nb200_ctx* ctx);
  *   "sym_algo"    how the pair-symmetric kernel sums the reactions on the streamed sources: 0 shared-memory transpose,
  *                 1 register rotation through the warp, 2 (FP32 default) rotation with decoupled hand-over
  *   "sym_ti", "sym_block"  register-block shape of the pair-symmetric kernel: targets per thread x threads per CTA.
- *                 FP32: 8 x 128 (default), 4 x 256, 4 x 128 (default up to 24576 bodies per shard); FP64: 4 x 256, 2 x 256, 2 x 128
+ *                 FP32: 8 x 128 (default), 4 x 256, 4 x 128 (default up to 24576 bodies per shard); FP64: 8 x 128 (default),
+ *                 4 x 256, 4 x 128, 2 x 256, 2 x 128 (the 8 x 128 and 4 x 128 FP64 shapes exist for the rotation, sym_algo 1)
  *   "seg_tiles" / "seg_sub"  source tiles / sub-tiles (128 sources FP32, 64 FP64) per work unit
  *   "variant"     index into the compiled (targets/thread, j-split, block) table of the ordered pass, -1 = auto
  *   "grid_mult"   ordered pass: persistent CTAs = grid_mult * (SMs * occupancy) / 16  (16 = exactly resident)
@@ -240,7 +241,9 @@ long long nb200_launch_count(const nb200_ctx* ctx);
  *   "pdl"         0 = no programmatic dependent launch between the pair-symmetric pass and its finish kernel (default on)
  *   "spin_timeout_ms"  bound of every device-side wait on a peer's flag (default 30000): when it expires the call returns
  *                 NB200_ESTATE naming the peer and what was awaited, and the context refuses further work
- *   "trace"       1 = append a CUDA-event timeline of shard 0 to nb200_plan() after nb200_step
+ *   "trace"       1 = append a CUDA-event timeline of shard 0 to nb200_plan() after nb200_step.  Independently of it every
+ *                 entry point that touches the device opens an NVTX range of its own name (visible in Nsight Systems;
+ *                 a no-op without a tool attached)
  *   "sym_itile"   256 = one-source-tile i-tiles (4 x 64 threads, transpose flavour): a small-N experiment kept for measurements
  *   "debug_fake_peer"  test hook for the time-out path on one GPU (a detached shard waits for a peer that does not exist)
  * All ranks of a sharded run must set the same options.  Returns NB200_EINVAL for an unknown key. */

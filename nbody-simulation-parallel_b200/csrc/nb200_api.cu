@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1284,6 +1285,15 @@ int finish_upload(nb200_ctx* ctx) {
 }  // namespace
 
 // =============================================================================== C ABI
+// NVTX range around every public entry point that touches the device (header-only NVTX v3: a no-op until a tool such
+// as Nsight Systems injects itself; SURVEY 5 "tracing").  The CUDA-event timeline of option "trace" is independent.
+struct NbRange {
+    explicit NbRange(const char* name) { nvtxRangePushA(name); }
+    ~NbRange() { nvtxRangePop(); }
+    NbRange(const NbRange&) = delete;
+    NbRange& operator=(const NbRange&) = delete;
+};
+
 extern "C" {
 
 const char* nb200_version(void) { return NB200_VERSION_STR; }
@@ -1332,6 +1342,7 @@ int nb200_ipc_export(nb200_ctx* ctx, void* blob) {
 }
 
 int nb200_ipc_attach(nb200_ctx* ctx, const void* blobs, int count) {
+    NbRange nvtx_range("nb200_ipc_attach");
     if (!ctx || !blobs) return NB200_EINVAL;
     if (!ctx->rank_mode) return fail(ctx, NB200_ESTATE, "ipc attach is for nb200_create_rank contexts");
     if (count != ctx->world) return fail(ctx, NB200_EINVAL, "expected %d blobs, got %d", ctx->world, count);
@@ -1541,6 +1552,7 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
 }
 
 int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
+    NbRange nvtx_range("nb200_upload_aos");
     if (!ctx) return NB200_EINVAL;
     if (ctx->dead) return fail(ctx, NB200_ESTATE, "context is unusable after a peer handshake timeout: destroy it");
     const int D = ctx->dim;
@@ -1573,6 +1585,7 @@ int nb200_upload_aos(nb200_ctx* ctx, const void* bodies, size_t stride) {
 }
 
 int nb200_generate(nb200_ctx* ctx, int kind, unsigned long long seed, double G) {
+    NbRange nvtx_range("nb200_generate");
     if (!ctx) return NB200_EINVAL;
     if (ctx->dead) return fail(ctx, NB200_ESTATE, "context is unusable after a peer handshake timeout: destroy it");
     const int D = ctx->dim;
@@ -1602,6 +1615,7 @@ int nb200_generate(nb200_ctx* ctx, int kind, unsigned long long seed, double G) 
 }
 
 int nb200_download_aos(nb200_ctx* ctx, void* bodies, size_t stride) {
+    NbRange nvtx_range("nb200_download_aos");
     if (!ctx) return NB200_EINVAL;
     if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "download before upload");
     const int D = ctx->dim;
@@ -1644,6 +1658,7 @@ int nb200_download_aos(nb200_ctx* ctx, void* bodies, size_t stride) {
 static inline double effective_cutoff(double c) { return c > 1e-20 ? c : 1e-20; }
 
 int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out) {
+    NbRange nvtx_range("nb200_forces");
     if (!ctx) return NB200_EINVAL;
     if (ctx->dead) return fail(ctx, NB200_ESTATE, "context is unusable after a peer handshake timeout: destroy it");
     cutoff_r2 = effective_cutoff(cutoff_r2);
@@ -1681,6 +1696,7 @@ int nb200_forces(nb200_ctx* ctx, double G, double cutoff_r2, double* forces_out)
 }
 
 int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps) {
+    NbRange nvtx_range("nb200_step");
     if (!ctx) return NB200_EINVAL;
     if (ctx->dead) return fail(ctx, NB200_ESTATE, "context is unusable after a peer handshake timeout: destroy it");
     cutoff_r2 = effective_cutoff(cutoff_r2);
@@ -1836,6 +1852,7 @@ int nb200_step(nb200_ctx* ctx, double G, double cutoff_r2, double dt, int nsteps
 }
 
 int nb200_energy(nb200_ctx* ctx, double G, double cutoff_r2, double* kinetic, double* potential) {
+    NbRange nvtx_range("nb200_energy");
     if (!ctx || !kinetic || !potential) return NB200_EINVAL;
     if (!ctx->uploaded) return fail(ctx, NB200_ESTATE, "energy before upload");
     cutoff_r2 = effective_cutoff(cutoff_r2);
@@ -1932,6 +1949,7 @@ int nb200_measure_fp32_peak(int device, double* tflops) {
 }
 
 int nb200_accuracy_pct(nb200_ctx* ctx, const double* forces, const double* reference, double* pct) {
+    NbRange nvtx_range("nb200_accuracy_pct");
     if (!ctx || !pct || (ctx->n && !reference)) return NB200_EINVAL;
     const int D = ctx->dim;
     unsigned long long ok = 0;
@@ -1964,6 +1982,7 @@ int nb200_accuracy_pct(nb200_ctx* ctx, const double* forces, const double* refer
 }
 
 int nb200_compare_forces(nb200_ctx* ctx, nb200_ctx* other, double* stats_out) {
+    NbRange nvtx_range("nb200_compare_forces");
     if (!ctx || !other || !stats_out) return NB200_EINVAL;
     if (ctx->dim != other->dim || ctx->n != other->n || ctx->shards.size() != other->shards.size() ||
         ctx->world != other->world)
@@ -2010,6 +2029,7 @@ int nb200_p2p_leaves(int device, int dim, size_t n, const void* bodies, size_t s
                      const long long* leaf_offsets, const long long* leaf_bodies, const long long* nbr_offsets,
                      const long long* nbr_leaves, double G, double cutoff_r2, double eps_same, int skip_same_index, int sign,
                      double* forces_out, double* kernel_ms) {
+    NbRange nvtx_range("nb200_p2p_leaves");
     nb200_ctx* ctx = nullptr;              // errors of this context-free call go to nb200_last_error(NULL)
     if (dim != 2 && dim != 3) return fail(nullptr, NB200_EINVAL, "dim must be 2 or 3, got %d", dim);
     if (sign != 1 && sign != -1) return fail(nullptr, NB200_EINVAL, "sign must be +1 (attractive, tree codes) or -1 (brute-force convention)");
@@ -2113,6 +2133,7 @@ int nb200_p2p_leaves(int device, int dim, size_t n, const void* bodies, size_t s
 }
 
 int nb200_validation_forces(nb200_ctx* ctx, double* forces_out, long long* index_out, int cap) {
+    NbRange nvtx_range("nb200_validation_forces");
     if (!ctx || cap < 0 || (cap > 0 && (!forces_out || !index_out))) return NB200_EINVAL;
     const int D = ctx->dim;
     const long long n = (long long)ctx->n;
