@@ -382,20 +382,30 @@ def run_config(pkg, oracle, name, prec_list=(32, 64)):
 def fp32_population_error(pkg, bodies, dim):
     """FP32-mode forces of ALL bodies against FP64 contexts on the device (nb200_compare_forces): (a) the same
     float-quantised inputs -- the arithmetic error the FP32 contract is stated on -- and (b) the unrounded
-    inputs -- what the 24-bit quantisation of the positions adds."""
+    inputs -- what the 24-bit quantisation of the positions adds -- and (c) the unrounded inputs again with option
+    fp32_positions = 48, which removes that part (with the throughput of its forces call)."""
     gen = pkg.generators
     n = bodies.shape[0]
     rb = gen.round_to_float(bodies)
     out = {}
-    with pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as c32:
+    keep = ("bodies", "max", "over_1e-5", "over_1e-4", "over_1e-3", "nonfinite", "histogram")
+    with pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as c32, pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as c48:
         c32.upload(bodies)
         c32.forces()
+        c48.set_option("fp32_positions", 48)        # (c) FP32 pair arithmetic on 48-bit positions (hi + lo float pairs)
+        c48.upload(bodies)
+        c48.forces()
+        t0 = c48.last_elapsed_ms
         for key, src in (("vs_fp64_same_quantised_inputs", rb), ("vs_fp64_unrounded_inputs", bodies)):
             with pkg.NBodyCuda(dim, n, pkg.NB200_FP64) as c64:
                 c64.upload(src)
                 c64.forces()
                 st = c32.compare_forces(c64)
-            out[key] = {k: st[k] for k in ("bodies", "max", "over_1e-5", "over_1e-4", "over_1e-3", "nonfinite", "histogram")}
+                out[key] = {k: st[k] for k in keep}
+                if src is bodies:
+                    st = c48.compare_forces(c64)
+                    out["fp32_positions_48_vs_fp64_unrounded_inputs"] = dict(
+                        {k: st[k] for k in keep}, G_interactions_per_s=round(n * (n - 1.0) / t0 / 1e6, 1))
     return out
 
 

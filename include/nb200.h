@@ -48,8 +48,12 @@ typedef struct nb200_ctx nb200_ctx;
  *             (measured on all 2^20 bodies of the headline config: 4 bodies above 1e-5, maximum 1.6e-5).
  *             Against the reference on the UNROUNDED double inputs the position quantisation itself moves each
  *             near-neighbour term by ~4 * 2^-24 * |x| / r: at N = 2^20 in the unit cube 35 % of the bodies differ by
- *             more than 1e-5 (maximum 1.8e-3; nb200_compare_forces reports the histogram).  Use NB200_FP64 where
- *             that matters; the reference's own -a 1 criterion (1 % per component, utils.h:170-219) is met either way. */
+ *             more than 1e-5 (maximum 1.8e-3; nb200_compare_forces reports the histogram).  Where that matters use
+ *             NB200_FP64, or option "fp32_positions" = 48 (below): the same FP32 pair arithmetic on positions kept as
+ *             float PAIRS (hi + lo), differences taken as (hi_j - hi_i) + (lo_j - lo_i).  Then the band above holds
+ *             against the reference on the UNROUNDED inputs (measured on the same 2^20 bodies: 4 above 1e-5, maximum
+ *             2.3e-5) at 70 % of the FP32 throughput (2726 vs 3904 G interactions/s; FP64: 1706).  One GPU, pair-
+ *             symmetric pass.  The reference's own -a 1 criterion (1 % per component, utils.h:170-219) is met by all. */
 #define NB200_FP64 64
 #define NB200_FP32 32
 
@@ -241,6 +245,10 @@ long long nb200_launch_count(const nb200_ctx* ctx);
  *   "pdl"         0 = no programmatic dependent launch between the pair-symmetric pass and its finish kernel (default on)
  *   "spin_timeout_ms"  bound of every device-side wait on a peer's flag (default 30000): when it expires the call returns
  *                 NB200_ESTATE naming the peer and what was awaited, and the context refuses further work
+ *   "fp32_positions"  24 (default) or 48, NB200_FP32 contexts on one GPU, set BEFORE the upload: 48 keeps every scaled
+ *                 coordinate as two floats (the second row is written by the pack kernel and by the integrator every
+ *                 step) so that the 24-bit quantisation of the positions no longer moves the near field; every pair takes
+ *                 the exact cut-off (no pre-pass); excludes "deterministic"
  *   "trace"       1 = append a CUDA-event timeline of shard 0 to nb200_plan() after nb200_step.  Independently of it every
  *                 entry point that touches the device opens an NVTX range of its own name (visible in Nsight Systems;
  *                 a no-op without a tool attached)

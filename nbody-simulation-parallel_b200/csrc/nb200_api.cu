@@ -170,6 +170,7 @@ struct Shard {
     std::vector<NbSymRow> sym_rows_host;
     std::vector<int> sym_prefix_host;
     int sym_key_seg = 0, sym_key_world = 0, sym_key_tpi = 0;
+    float* src_lo[2] = {nullptr, nullptr};   // 48-bit positions: lo parts of the scaled coordinates, tile-planar [D][256]
     const void* occ_fn = nullptr;        // pair-symmetric kernel of the last occupancy query and its answer
     int occ_blocks = 0;
     double* gacc = nullptr;                           // [3][nalloc]
@@ -234,6 +235,7 @@ struct nb200_ctx {
     bool dead = false;            // a peer handshake timed out: the ranks' step counters may have diverged
     // options
     int opt_variant = -1, opt_seg_tiles = 0, opt_grid_mult = 0, opt_overlap = -1, opt_trace = 0, opt_detect = -1, opt_symmetric = -1, opt_sym_ti = 0, opt_sym_itile = 0, opt_sym_algo = -1, opt_sym_block = 0, opt_seg_sub = 0, opt_shard_upload = -1, opt_pdl = -1, opt_eqm = -1, opt_deterministic = 0;
+    bool opt_pos48 = false;          // FP32 mode with 48-bit positions (hi + lo float pairs): option "fp32_positions"
     long opt_spin_timeout_ms = 30000;   // bound of every device-side wait on a peer's flag
     std::vector<std::pair<std::string, cudaEvent_t>> trace;   // shard-0 timeline of the last step call (opt_trace)
     // bookkeeping
@@ -308,7 +310,8 @@ template <int D> SymKernel sym_kernel_eqm(bool f64, SymShape sh) {
     if (f64) return sh.ti == 8 ? nb_force_sym_kernel<D, true, 8, 128, 1, true> : nb_force_sym_kernel<D, true, 4, 256, 1, true>;
     return sh.ti == 8 ? nb_force_sym_kernel<D, false, 8, 128, 2, true> : nb_force_sym_kernel<D, false, 4, 128, 2, true>;
 }
-SymKernel pick_sym_kernel(int dim, bool f64, SymShape sh, int algo, bool eqm = false) {
+SymKernel pick_sym_kernel(int dim, bool f64, SymShape sh, int algo, bool eqm = false, bool hl = false) {
+    if (hl) return dim == 3 ? nb_force_sym_kernel<3, false, 8, 128, 2, false, true> : nb_force_sym_kernel<2, false, 8, 128, 2, false, true>;
     if (eqm && sym_has_eqm(f64, sh, algo)) return dim == 3 ? sym_kernel_eqm<3>(f64, sh) : sym_kernel_eqm<2>(f64, sh);
     if (dim == 3) return f64 ? sym_kernel_of<3, true>(sh, algo) : sym_kernel_of<3, false>(sh, algo);
     return f64 ? sym_kernel_of<2, true>(sh, algo) : sym_kernel_of<2, false>(sh, algo);
@@ -424,6 +427,9 @@ int alloc_shard(nb200_ctx* ctx, Shard& s) {
                 CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, ctx->f64, sh, algo, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo)));
     }
+    if (!ctx->f64)
+        CK(cudaFuncSetAttribute((const void*)pick_sym_kernel(D, false, SymShape{8, 128}, 2, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)nb_sym_smem_bytes(D, 128, false, 8, 2, true)));
     return preload_aux_kernels(ctx);
 }
 
@@ -444,6 +450,7 @@ void free_shard(Shard& s) {
     cudaFree(s.det_slots);
     cudaFree(s.grid_keys); cudaFree(s.suspect); cudaFree(s.sym_rows); cudaFree(s.sym_prefix); cudaFree(s.gacc); cudaFree(s.sym_done);
     for (int b = 0; b < 2; ++b) cudaFree(s.src[b]);
+    for (int b = 0; b < 2; ++b) cudaFree(s.src_lo[b]);
     cudaFree(s.acc); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.mass); cudaFree(s.forces);
     cudaFree(s.aos_dev); cudaFree(s.energy); cudaFree(s.bounds); cudaFree(s.cmp); cudaFree(s.tile_done); cudaFree(s.sched);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
@@ -499,6 +506,7 @@ struct Plan {
 // pays from N ~ 50000: measured at N = 65536, FP32: 1.275 vs 1.296 ms/step in 3D, 0.944 vs 1.002 in 2D; at 32768 (3D) it
 // loses, 0.432 vs 0.351 (profiles/r02/small_n.md).
 bool use_detect(const nb200_ctx* ctx) {
+    if (ctx->opt_pos48) return false;        // the pre-pass sees the hi parts only: every pair takes the exact cut-off
     if (ctx->opt_detect >= 0) return ctx->opt_detect != 0;
     return ctx->n >= 49152u;
 }
@@ -758,6 +766,7 @@ int launch_pass(nb200_ctx* ctx, Shard& s, const Plan& pl, const Ranges& rg, unsi
 // pair, ~10 % slower than the plain chains, but 7.5 instead of 11 FMA-pipe lane-ops per interaction and no extra launches)
 constexpr size_t kSymMinN = 12288;
 bool use_symmetric(const nb200_ctx* ctx, bool stepping) {
+    if (ctx->opt_pos48) return true;         // the 48-bit flavour exists in the pair-symmetric kernel only (one shard)
     if (ctx->opt_symmetric == 0 || ctx->opt_deterministic) return false;
     if (ctx->opt_symmetric < 0 && !use_detect(ctx) && ctx->n < kSymMinN) return false;
     if (ctx->opt_symmetric > 0 && !use_detect(ctx) && ctx->opt_detect != 0 && ctx->n < kSymMinN) return false;   // explicit 1 keeps meaning "when the pre-pass runs" below the threshold
@@ -848,7 +857,7 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     //         (one CTA per SM), 4 x 128 (three), 2 x 256 and 2 x 128 (two / four CTAs per SM under 128 registers)
     // opt-in shape for small problems on one shard: i-tiles of ONE source tile (4 targets x 64 threads, many
     // small CTAs); option "sym_itile" = 256 selects it
-    const bool small = !cross && (ctx->opt_sym_itile ? ctx->opt_sym_itile == 256 : (kSymSmallN > 0 && ctx->n < kSymSmallN));
+    const bool small = !cross && !ctx->opt_pos48 && (ctx->opt_sym_itile ? ctx->opt_sym_itile == 256 : (kSymSmallN > 0 && ctx->n < kSymSmallN));
     SymShape sh{4, 64};
     if (!small) {
         if (ctx->f64) {
@@ -859,7 +868,7 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
             sh.block = sh.ti == 8 ? 128 : ctx->opt_sym_block == 128 ? 128 : 256;
         }
     }
-    const int algo = small ? 0 : std::min(ctx->opt_sym_algo >= 0 ? ctx->opt_sym_algo : kSymAlgoDefault, ctx->f64 ? 1 : 2);
+    const int algo = ctx->opt_pos48 ? 2 : small ? 0 : std::min(ctx->opt_sym_algo >= 0 ? ctx->opt_sym_algo : kSymAlgoDefault, ctx->f64 ? 1 : 2);
     // FP64: the 8 x 128 and 4 x 128 shapes exist for the rotation only
     if (!small && ctx->f64 && algo == 0 && sh.ti >= 4) sh = SymShape{4, 256};
     const int subt = nb_sym_subtiles(ctx->f64, algo);
@@ -867,15 +876,18 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     // up to N ~ 24576 (N=16384: 0.108 ms/step vs 0.112 with 8 x 128)
     if (!small && !ctx->f64 && !ctx->opt_sym_ti && !ctx->opt_sym_block && !cross && (long long)tiles * NB_TILE <= 24576)
         sh = SymShape{4, 128};
-    const bool eqm = ctx->equal_mass && sym_has_eqm(ctx->f64, sh, algo);
+    // 48-bit positions: one flavour (8 x 128, decoupled rotation, general masses, exact cut-off)
+    const bool hl = ctx->opt_pos48;
+    if (hl) sh = SymShape{8, 128};
+    const bool eqm = !hl && ctx->equal_mass && sym_has_eqm(ctx->f64, sh, algo);
     int resident = 0;
     {
         // asked once per kernel, not once per step: the query is a driver call of several microseconds (more once other
         // lazily loaded modules live in the context), and a 0.1 ms step has no host time to spare
-        const void* fn = (const void*)pick_sym_kernel(D, ctx->f64, sh, algo, eqm);
+        const void* fn = (const void*)pick_sym_kernel(D, ctx->f64, sh, algo, eqm, hl);
         if (s.occ_fn != fn) {
             int nb = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, sh.block, nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, sh.block, nb_sym_smem_bytes(D, sh.block, ctx->f64, sh.ti, algo, hl)));
             s.occ_fn = fn;
             s.occ_blocks = std::max(1, nb);
         }
@@ -892,13 +904,14 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
     const int ti = sh.ti, block = sh.block;
     const int itile = ti * block;
     const int seg_ord = std::max(1, seg_sub / subt);
-    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, sh, algo, eqm);
-    const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64, ti, algo);
+    const SymKernel kfn = pick_sym_kernel(D, ctx->f64, sh, algo, eqm, hl);
+    const size_t smem = nb_sym_smem_bytes(D, block, ctx->f64, ti, algo, hl);
     if (int rc = build_sym_rows(ctx, s, seg_sub, seg_ord, subt, cross, itile / NB_TILE)) return rc;
     const int seg = seg_sub;
     NbSymParams Q;
     memset(&Q, 0, sizeof Q);
     Q.src = s.src[cur];
+    Q.src_lo = hl ? s.src_lo[cur] : nullptr;
     Q.gacc = s.gacc;
     Q.gstride = (size_t)ctx->nalloc;
     Q.sched = s.sched;
@@ -920,6 +933,7 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
 
     NbSymFinish F;
     memset(&F, 0, sizeof F);
+    F.lo_next = (hl && mode != 0) ? s.src_lo[cur ^ 1] : nullptr;
     F.gacc = s.gacc;
     F.gstride = (size_t)ctx->nalloc;
     F.count = tiles * NB_TILE;
@@ -978,6 +992,7 @@ int launch_symmetric(nb200_ctx* ctx, Shard& s, int mode, double G, double cutoff
                  ctx->ntiles, with_flags ? "grid-prepass(plain|exact)" : "exact",
                  cross ? " + reaction sums pushed to their owners over NVLink" : "");
         if (eqm) strncat(buf, " [equal-mass chains]", sizeof buf - strlen(buf) - 1);
+        if (hl) strncat(buf, " [48-bit positions]", sizeof buf - strlen(buf) - 1);
         ctx->plan = buf;
     }
     return NB200_OK;
@@ -1088,6 +1103,16 @@ int pack_sources(nb200_ctx* ctx) {
         }
         CK(cudaGetLastError());
         ctx->launches++;
+        if (ctx->opt_pos48) {
+            const size_t lo_bytes = (size_t)ctx->nalloc * D * sizeof(float);
+            for (int b = 0; b < 2; ++b)
+                if (!s.src_lo[b]) CK(cudaMalloc(&s.src_lo[b], lo_bytes));
+            const int blocks = (int)((ctx->nalloc + threads - 1) / threads);
+            if (D == 3) nb_pack_lo_kernel<3><<<blocks, threads, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, ctx->nalloc, s.src_lo[0], s.src_lo[1], ctx->pos_scale);
+            else nb_pack_lo_kernel<2><<<blocks, threads, 0, s.compute>>>(s.aos_dev, sd, (long long)ctx->n, ctx->nalloc, s.src_lo[0], s.src_lo[1], ctx->pos_scale);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
     }
     for (Shard& s : ctx->shards) {
         CK(cudaSetDevice(s.device));
@@ -1513,7 +1538,22 @@ int nb200_set_option(nb200_ctx* ctx, const char* key, long value) {
             return fail(ctx, NB200_ESTATE, "set 'equal_mass' before the upload (it decides where the padding bodies go)");
         ctx->opt_eqm = value < 0 ? -1 : (value != 0);
     }
-    else if (!strcmp(key, "deterministic")) ctx->opt_deterministic = value != 0;
+    else if (!strcmp(key, "deterministic")) {
+        if (value != 0 && ctx->opt_pos48) return fail(ctx, NB200_EINVAL, "'deterministic' and 'fp32_positions' = 48 exclude each other");
+        ctx->opt_deterministic = value != 0;
+    }
+    else if (!strcmp(key, "fp32_positions")) {
+        // 48: FP32 pair arithmetic on positions kept as float pairs (hi + lo); 24: the plain FP32 mode
+        if (value != 24 && value != 48) return fail(ctx, NB200_EINVAL, "fp32_positions is 24 or 48");
+        if (value == 48) {
+            if (ctx->f64) return fail(ctx, NB200_EINVAL, "fp32_positions applies to NB200_FP32 contexts");
+            if (ctx->world != 1 || ctx->shards.size() != 1) return fail(ctx, NB200_EINVAL, "fp32_positions = 48 runs on one shard (the lo rows are not exchanged)");
+            if (ctx->opt_deterministic) return fail(ctx, NB200_EINVAL, "'deterministic' and 'fp32_positions' = 48 exclude each other");
+        }
+        if (ctx->uploaded && (value == 48) != ctx->opt_pos48)
+            return fail(ctx, NB200_ESTATE, "set 'fp32_positions' before the upload (the lo rows are written by the pack kernel)");
+        ctx->opt_pos48 = value == 48;
+    }
     else if (!strcmp(key, "pdl")) ctx->opt_pdl = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "shard_upload")) ctx->opt_shard_upload = value < 0 ? -1 : (value != 0);
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = (int)std::max(0L, value);

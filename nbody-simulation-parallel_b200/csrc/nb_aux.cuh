@@ -49,6 +49,26 @@ __global__ void nb_pack_kernel(const double* __restrict__ aos, size_t stride_d, 
     }
 }
 
+// 48-bit positions (option "fp32_positions" = 48): the part of every scaled coordinate the float row loses, as a second
+// float, tile-planar [D][256] per tile, both buffers.  Padding bodies get 0.
+template <int D>
+__global__ void nb_pack_lo_kernel(const double* __restrict__ aos, size_t stride_d, long long n, long long nalloc,
+                                  float* __restrict__ lo0, float* __restrict__ lo1, double pos_scale) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nalloc) return;
+    const size_t off = (size_t)(b / NB_TILE) * (NB_TILE * D) + (b % NB_TILE);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        float lo = 0.f;
+        if (b < n) {
+            const double xs = aos[(size_t)b * stride_d + d] * pos_scale;
+            lo = (float)(xs - (double)(float)xs);
+        }
+        lo0[off + (size_t)d * NB_TILE] = lo;
+        lo1[off + (size_t)d * NB_TILE] = lo;
+    }
+}
+
 // Shard-local flavour (multi-GPU with the peer-store exchange): the image holds only the rows this shard owns; their
 // tile-planar source rows go to BOTH buffers of this shard and of every peer (plain stores on peer-mapped pointers over
 // NVLink), so no rank ever uploads or packs a body it does not own.  Thread t < tpad: own padded row t (rows past the

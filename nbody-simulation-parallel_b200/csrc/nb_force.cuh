@@ -48,13 +48,19 @@ enum { NB_PLAIN = 0, NB_TRACKED = 1, NB_EXACT = 2 };
 
 // EQM (equal-mass system, see nb_force_sym.cuh): the sums are taken WITHOUT the source masses (s = 1/r^4), the common
 // mass is applied once per body in the epilogue.
-template <int D, int TI, int JS, int MODE, int UNR, bool EQM = false>
+// HL (48-bit positions, see nb_force_sym.cuh): lo planes behind the D + 1 hi planes of the stage, nlo = negated lo parts
+// of the targets.
+template <int D, int TI, int JS, int MODE, int UNR, bool EQM = false, bool HL = false>
 __device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, int part, float cutoff,
-                                             const float (&npos)[TI][3], float2 (&a)[TI][3]) {
+                                             const float (&npos)[TI][3], float2 (&a)[TI][3],
+                                             const float (*nlo)[3] = nullptr) {
     const float4* sx = reinterpret_cast<const float4*>(stage);
     const float4* sy = sx + NB_TILE / 4;
     const float4* sz = sy + NB_TILE / 4;                      // D == 3 only
     const float4* sm = sx + D * (NB_TILE / 4);
+    const float4* lx = sm + NB_TILE / 4;                      // HL only
+    const float4* ly = lx + NB_TILE / 4;
+    const float4* lz = ly + NB_TILE / 4;
 #pragma unroll
     for (int t = 0; t < TI; ++t)
 #pragma unroll
@@ -67,21 +73,35 @@ __device__ __forceinline__ float nb_tile_f32(const float* __restrict__ stage, in
         const float4 X = sx[q], Y = sy[q], M = sm[q];
         float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
         if (D == 3) Z = sz[q];
+        float4 XL = make_float4(0.f, 0.f, 0.f, 0.f), YL = XL, ZL = XL;
+        if (HL) {
+            XL = lx[q];
+            YL = ly[q];
+            if (D == 3) ZL = lz[q];
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const float2 xs = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
             const float2 ys = h ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
             const float2 zs = h ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
             const float2 ms = h ? make_float2(M.z, M.w) : make_float2(M.x, M.y);
+            const float2 xl = h ? make_float2(XL.z, XL.w) : make_float2(XL.x, XL.y);
+            const float2 yl = h ? make_float2(YL.z, YL.w) : make_float2(YL.x, YL.y);
+            const float2 zl = h ? make_float2(ZL.z, ZL.w) : make_float2(ZL.x, ZL.y);
 #pragma unroll
             for (int t = 0; t < TI; ++t) {
-                const float2 dx = __fadd2_rn(xs, make_float2(npos[t][0], npos[t][0]));
-                const float2 dy = __fadd2_rn(ys, make_float2(npos[t][1], npos[t][1]));
+                float2 dx = __fadd2_rn(xs, make_float2(npos[t][0], npos[t][0]));
+                float2 dy = __fadd2_rn(ys, make_float2(npos[t][1], npos[t][1]));
+                if (HL) {
+                    dx = __fadd2_rn(dx, __fadd2_rn(xl, make_float2(nlo[t][0], nlo[t][0])));
+                    dy = __fadd2_rn(dy, __fadd2_rn(yl, make_float2(nlo[t][1], nlo[t][1])));
+                }
                 float2 r2 = __fmul2_rn(dx, dx);
                 r2 = __ffma2_rn(dy, dy, r2);
                 float2 dz;
                 if (D == 3) {
                     dz = __fadd2_rn(zs, make_float2(npos[t][2], npos[t][2]));
+                    if (HL) dz = __fadd2_rn(dz, __fadd2_rn(zl, make_float2(nlo[t][2], nlo[t][2])));
                     r2 = __ffma2_rn(dz, dz, r2);
                 }
                 if (MODE == NB_EXACT) {

@@ -53,6 +53,7 @@ __host__ __device__ constexpr int nb_sym_subtiles(bool f64, int algo) { return a
 
 struct NbSymParams {
     const void* src;             // tile-planar sources (current step), all bodies (float or double)
+    const float* src_lo;         // HL flavour: the lo parts of the scaled coordinates, tile-planar [D][256] per tile
     double* gacc;                // [3][gstride] FP64 accumulators indexed by GLOBAL body index
     size_t gstride;
     unsigned* sched;             // [2] unit counter + exit counter (self-resetting)
@@ -95,6 +96,7 @@ struct NbSymFinish {
     unsigned long long seq;      // 0 = nothing to wait for
     int count;
     unsigned* done;              // CTA completion counter for the step signal (self-resetting)
+    float* lo_next;              // 48-bit positions: lo rows of the next step's sources (null otherwise)
 };
 
 // TMA ring depth of a shape: the 4 x 128 FP32 shape was sized for five CTAs per SM (two stages); it runs four now
@@ -119,11 +121,11 @@ __host__ __device__ constexpr int nb_sym_min_blocks(bool f64, int ti, int block,
                  : block == 256 ? 2 : (ti == 8 ? ((dim == 3 && !eqm) ? 2 : 3) : NB_SYM_MB_4X128);
 }
 
-static inline size_t nb_sym_smem_bytes(int dim, int block, bool f64, int ti = 0, int algo = 0) {
+static inline size_t nb_sym_smem_bytes(int dim, int block, bool f64, int ti = 0, int algo = 0, bool hl = false) {
     const size_t rs = f64 ? 8 : 4;
     if (ti == 0) ti = block == 64 ? 4 : NB_SYM_ITILE / block;
     const int stages = nb_sym_stages(f64, ti, block);
-    const size_t ring = (size_t)stages * NB_TILE * (dim + 1) * rs;
+    const size_t ring = (size_t)stages * NB_TILE * (dim + 1 + (hl ? dim : 0)) * rs;
     const size_t bars = 2 * stages * sizeof(uint64_t) + 16;
     // transpose scratch of sym_algo 0; the rotation flavours keep the FP64 per-target sums there
     // ([TI * 3][block] doubles)
@@ -256,17 +258,25 @@ __device__ __forceinline__ void nb_tile_f32_sym(const float* __restrict__ stage,
 //   EQM = true      : equal-mass system (every real body has the same mass, padding bodies are parked out of range):
 //                     s = u = 1/r^4, the two mass multiplies leave the chain (13 instead of 15 packed instructions
 //                     per two pairs) and the common mass is applied once per body by the finish kernel
-template <int D, int TI, int MODE, bool DECOUPLE, bool EQM = false>
+//   HL = true       : 48-bit positions (option "fp32_positions" = 48): every coordinate is a float pair hi + lo; the
+//                     difference is (hi_j - hi_i) + (lo_j - lo_i) -- the first term is exact for close pairs, so the
+//                     24-bit quantisation of the positions no longer moves the near field (2 FADD2 more per coordinate:
+//                     21 instead of 15 packed instructions per two pairs).  The lo planes follow the D + 1 hi planes
+//                     in the stage; nlo holds the negated lo parts of the targets.
+template <int D, int TI, int MODE, bool DECOUPLE, bool EQM = false, bool HL = false>
 __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ stage, float cutoff,
                                                     const float (&npos)[TI][3],
                                                     const float (&mi)[TI],
                                                     float2 (&a)[TI][3], float* __restrict__ wout, int lane,
-                                                    int hf_begin, int hf_end) {
+                                                    int hf_begin, int hf_end, const float (*nlo)[3] = nullptr) {
     // plane p of the stage as float4: home group g of half tile hf sits at p * (NB_TILE / 4) + 32 hf + g
     const float4* sx = reinterpret_cast<const float4*>(stage);
     const float4* sy = sx + NB_TILE / 4;
     const float4* sz = sy + NB_TILE / 4;                      // D == 3 only
     const float4* sm = sx + D * (NB_TILE / 4);
+    const float4* lx = sm + NB_TILE / 4;                      // HL only: lo planes
+    const float4* ly = lx + NB_TILE / 4;
+    const float4* lz = ly + NB_TILE / 4;
 #pragma unroll
     for (int t = 0; t < TI; ++t)
 #pragma unroll
@@ -275,16 +285,22 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
     const int from = (lane + 1) & 31;
 
     // the TI chains of one pair of sources: target sums a, reaction sums b
-    auto chains = [&](const float2 xs, const float2 ys, const float2 zs, const float2 ms, float2 (&b)[3]) {
+    auto chains = [&](const float2 xs, const float2 ys, const float2 zs, const float2 ms, float2 (&b)[3],
+                      const float2 xl, const float2 yl, const float2 zl) {
 #pragma unroll
         for (int t = 0; t < TI; ++t) {
-            const float2 dx = __fadd2_rn(xs, make_float2(npos[t][0], npos[t][0]));
-            const float2 dy = __fadd2_rn(ys, make_float2(npos[t][1], npos[t][1]));
+            float2 dx = __fadd2_rn(xs, make_float2(npos[t][0], npos[t][0]));
+            float2 dy = __fadd2_rn(ys, make_float2(npos[t][1], npos[t][1]));
+            if (HL) {
+                dx = __fadd2_rn(dx, __fadd2_rn(xl, make_float2(nlo[t][0], nlo[t][0])));
+                dy = __fadd2_rn(dy, __fadd2_rn(yl, make_float2(nlo[t][1], nlo[t][1])));
+            }
             float2 r2 = __fmul2_rn(dx, dx);
             r2 = __ffma2_rn(dy, dy, r2);
             float2 dz;
             if (D == 3) {
                 dz = __fadd2_rn(zs, make_float2(npos[t][2], npos[t][2]));
+                if (HL) dz = __fadd2_rn(dz, __fadd2_rn(zl, make_float2(nlo[t][2], nlo[t][2])));
                 r2 = __ffma2_rn(dz, dz, r2);
             }
             if (MODE == NB_EXACT) {
@@ -333,16 +349,25 @@ __device__ __forceinline__ void nb_tile_f32_sym_rot(const float* __restrict__ st
             const float4 X = sx[q], Y = sy[q], M = sm[q];
             float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
             if (D == 3) Z = sz[q];
+            float4 XL = make_float4(0.f, 0.f, 0.f, 0.f), YL = XL, ZL = XL;
+            if (HL) {
+                XL = lx[q];
+                YL = ly[q];
+                if (D == 3) ZL = lz[q];
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const float2 xs = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
                 const float2 ys = h ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
                 const float2 zs = h ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
                 const float2 ms = h ? make_float2(M.z, M.w) : make_float2(M.x, M.y);
+                const float2 xl = h ? make_float2(XL.z, XL.w) : make_float2(XL.x, XL.y);
+                const float2 yl = h ? make_float2(YL.z, YL.w) : make_float2(YL.x, YL.y);
+                const float2 zl = h ? make_float2(ZL.z, ZL.w) : make_float2(ZL.x, ZL.y);
                 float2 b[3];
 #pragma unroll
                 for (int d = 0; d < 3; ++d) b[d] = DECOUPLE ? zero2 : trav[h][d];
-                chains(xs, ys, zs, ms, b);
+                chains(xs, ys, zs, ms, b, xl, yl, zl);
                 hand_over(trav[h], b);
             }
         }
@@ -512,10 +537,13 @@ __device__ __forceinline__ void nb_tile_f64_sym_rot(const double* __restrict__ s
 }
 
 // ALGO: 0 = shared-memory transpose of the reaction sums, 1 = register rotation, 2 (FP32) = rotation, decoupled
-template <int D, bool F64, int TI, int BLOCK, int ALGO = 0, bool EQM = false>
+//       HL (FP32 rotation, general masses): 48-bit positions -- a stage holds the D + 1 hi planes of a tile followed by
+//       its D lo planes (two bulk copies on one barrier), the exact cut-off is applied to every pair
+template <int D, bool F64, int TI, int BLOCK, int ALGO = 0, bool EQM = false, bool HL = false>
 __global__ void __launch_bounds__(BLOCK, nb_sym_min_blocks(F64, TI, BLOCK, D, EQM))
 nb_force_sym_kernel(const NbSymParams P) {
     static_assert(!EQM || ALGO != 0, "the equal-mass flavour exists for the rotation flavours only");
+    static_assert(!HL || (!F64 && ALGO == 2 && !EQM), "48-bit positions: FP32, decoupled rotation, general masses");
     constexpr int STAGES = nb_sym_stages(F64, TI, BLOCK);
     using real = typename NbReal<F64>::type;
     constexpr int NP = D + 1;
@@ -523,11 +551,14 @@ nb_force_sym_kernel(const NbSymParams P) {
     static_assert(ITILE % NB_TILE == 0, "an i-tile is a whole number of source tiles");
     constexpr int TILE_ELEMS = NB_TILE * NP;
     constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(real);
+    constexpr int LO_ELEMS = HL ? NB_TILE * D : 0;
+    constexpr uint32_t LO_BYTES = LO_ELEMS * sizeof(real);
+    constexpr int STAGE_ELEMS = TILE_ELEMS + LO_ELEMS;
     constexpr int NWARPS = BLOCK / 32;
 
     extern __shared__ __align__(128) unsigned char nb_smem[];
     real* ring = reinterpret_cast<real*>(nb_smem);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(nb_smem + (size_t)STAGES * TILE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(nb_smem + (size_t)STAGES * STAGE_ELEMS * sizeof(real));
     uint64_t* empty_bar = full_bar + STAGES;
     int* s_unit = reinterpret_cast<int*>(empty_bar + STAGES);   // [0] i-tile (or -1), [1] segment
     float* scr_all = reinterpret_cast<float*>(s_unit + 4);
@@ -595,13 +626,17 @@ nb_force_sym_kernel(const NbSymParams P) {
                 const unsigned k = kt + t;
                 const int slot = k % STAGES;
                 nb_mbar_wait(&empty_bar[slot], ((k / STAGES) & 1u) ^ 1u);
-                nb_mbar_expect_tx(&full_bar[slot], TILE_BYTES);
-                nb_tma_load_1d(ring + (size_t)slot * TILE_ELEMS, src + (size_t)(ts + t) * TILE_ELEMS,
+                nb_mbar_expect_tx(&full_bar[slot], TILE_BYTES + LO_BYTES);
+                nb_tma_load_1d(ring + (size_t)slot * STAGE_ELEMS, src + (size_t)(ts + t) * TILE_ELEMS,
                                TILE_BYTES, &full_bar[slot]);
+                if constexpr (HL)
+                    nb_tma_load_1d(ring + (size_t)slot * STAGE_ELEMS + TILE_ELEMS,
+                                   reinterpret_cast<const real*>(P.src_lo) + (size_t)(ts + t) * LO_ELEMS, LO_BYTES, &full_bar[slot]);
             }
         }
 
         real tq[TI][3], mi[TI];          // FP32: NEGATED target coordinates (operand of the packed add); FP64: plain
+        float tlo[HL ? TI : 1][3];       // HL: negated lo parts
         int own_tile[TI];
         bool suspect = false;
 #pragma unroll
@@ -618,6 +653,10 @@ nb_force_sym_kernel(const NbSymParams P) {
             for (int d = 0; d < 3; ++d) {
                 const real x = (d < D) ? (live ? tb[d * NB_TILE] : park) : real(0);
                 tq[t][d] = F64 ? x : -x;
+                if constexpr (HL) {
+                    const float* tl = P.src_lo + (size_t)(b / NB_TILE) * LO_ELEMS + (b % NB_TILE);
+                    tlo[t][d] = (d < D && live) ? -tl[d * NB_TILE] : 0.f;
+                }
             }
             mi[t] = live ? tb[D * NB_TILE] : real(0);
             if (P.suspect) suspect |= P.suspect[it * ITILE + tid + t * BLOCK] != 0;
@@ -643,15 +682,19 @@ nb_force_sym_kernel(const NbSymParams P) {
                 const unsigned k = kt + t + STAGES - 1;
                 const int slot = k % STAGES;
                 nb_mbar_wait(&empty_bar[slot], ((k / STAGES) & 1u) ^ 1u);
-                nb_mbar_expect_tx(&full_bar[slot], TILE_BYTES);
-                nb_tma_load_1d(ring + (size_t)slot * TILE_ELEMS,
+                nb_mbar_expect_tx(&full_bar[slot], TILE_BYTES + LO_BYTES);
+                nb_tma_load_1d(ring + (size_t)slot * STAGE_ELEMS,
                                src + (size_t)(ts + t + STAGES - 1) * TILE_ELEMS, TILE_BYTES,
                                &full_bar[slot]);
+                if constexpr (HL)
+                    nb_tma_load_1d(ring + (size_t)slot * STAGE_ELEMS + TILE_ELEMS,
+                                   reinterpret_cast<const real*>(P.src_lo) + (size_t)(ts + t + STAGES - 1) * LO_ELEMS, LO_BYTES,
+                                   &full_bar[slot]);
             }
             const unsigned k = kt + t;
             const int slot = k % STAGES;
             nb_mbar_wait(&full_bar[slot], (k / STAGES) & 1u);
-            const real* stage = ring + (size_t)slot * TILE_ELEMS;
+            const real* stage = ring + (size_t)slot * STAGE_ELEMS;
             real* wout = bout_all + ((size_t)bbuf * NWARPS + warp) * (D * NB_TILE);
             // sub-tiles [h0, h1) of this tile belong to the unit (whole tile: [0, SUBT))
             const int h0 = sym ? max(s0 - (ts + t) * SUBT, 0) : 0;
@@ -692,11 +735,13 @@ nb_force_sym_kernel(const NbSymParams P) {
                         if (exact_tile) nb_tile_f32_sym<D, TI, NB_EXACT>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
                         else nb_tile_f32_sym<D, TI, NB_PLAIN>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
                     } else {
-                        if (exact_tile) nb_tile_f32_sym_rot<D, TI, NB_EXACT, ALGO == 2, EQM>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1);
+                        if constexpr (HL) nb_tile_f32_sym_rot<D, TI, NB_EXACT, true, false, true>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1, tlo);
+                        else if (exact_tile) nb_tile_f32_sym_rot<D, TI, NB_EXACT, ALGO == 2, EQM>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1);
                         else nb_tile_f32_sym_rot<D, TI, NB_PLAIN, ALGO == 2, EQM>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1);
                     }
                 } else {
-                    if (exact_tile) nb_tile_f32<D, TI, 1, NB_EXACT, 1, EQM>(fstage, 0, cutoff_f, npos, a);
+                    if constexpr (HL) nb_tile_f32<D, TI, 1, NB_EXACT, 1, false, true>(fstage, 0, cutoff_f, npos, a, tlo);
+                    else if (exact_tile) nb_tile_f32<D, TI, 1, NB_EXACT, 1, EQM>(fstage, 0, cutoff_f, npos, a);
                     else nb_tile_f32<D, TI, 1, NB_PLAIN, 1, EQM>(fstage, 0, cutoff_f, npos, a);
                 }
 #pragma unroll
@@ -829,6 +874,9 @@ __global__ void __launch_bounds__(256) nb_finish_kernel(const NbForceParams P, c
                     P.pos[(size_t)d * P.tpad + li] = x;
                     const real xs = (real)(x * P.pos_scale);
                     nb[d * NB_TILE] = xs;
+                    if (F.lo_next)
+                        F.lo_next[(size_t)(b / NB_TILE) * (NB_TILE * D) + (size_t)d * NB_TILE + (b % NB_TILE)] =
+                            (float)(x * P.pos_scale - (double)xs);
                     for (int pr = 0; pr < P.n_peers; ++pr)
                         static_cast<real*>(P.peer_next[pr])[off0 + (size_t)d * NB_TILE] = xs;
                 }

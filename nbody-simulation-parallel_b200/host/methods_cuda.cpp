@@ -79,14 +79,20 @@ struct PhaseTrace {
 // (re)creates the cached context when the problem shape changes
 nb200_ctx* acquire(int dim, std::size_t n) {
     Session& s = session();
+    // NB200_PRECISION: 64 (default), 32, or 48 = FP32 pair arithmetic on 48-bit positions (option fp32_positions)
     const int precision = env_int("NB200_PRECISION", NB200_FP64);
     const int gpus = env_int("NB200_GPUS", 1);
     if (s.ctx && s.dim == dim && s.n == n && s.precision == precision && s.gpus == gpus) return s.ctx;
     s.reset();
-    const int rc = nb200_create(&s.ctx, dim, n, precision, gpus);
+    int rc = nb200_create(&s.ctx, dim, n, precision == 48 ? NB200_FP32 : precision, gpus);
     if (rc != NB200_OK) {
         s.ctx = nullptr;
         raise("nb200_create", rc, nullptr);
+    }
+    if (precision == 48 && (rc = nb200_set_option(s.ctx, "fp32_positions", 48)) != NB200_OK) {
+        const std::string why = nb200_last_error(s.ctx);
+        s.reset();
+        throw std::runtime_error("BruteForce_CUDA: NB200_PRECISION=48: " + why);
     }
     s.dim = dim;
     s.n = n;
@@ -137,8 +143,8 @@ void brute_force_cuda_simulate(std::vector<Body<D>>& bodies, double dt, int step
 // One throw-away evaluation on a tiny body set per (dimension, precision): CUDA loads kernels lazily
 // on their first launch, which would otherwise land inside the first timed call of a process.
 void touch_kernels(int dim, int precision) {
-    static bool done[4][2] = {{false}};
-    bool& flag = done[dim][precision == NB200_FP32 ? 1 : 0];
+    static bool done[4][3] = {{false}};
+    bool& flag = done[dim][precision == NB200_FP32 ? 1 : precision == 48 ? 2 : 0];
     if (flag) return;
     flag = true;
     const std::size_t n = 2048;
@@ -150,7 +156,8 @@ void touch_kernels(int dim, int precision) {
     }
     std::vector<double> f(n * dim);
     nb200_ctx* t = nullptr;
-    if (nb200_create(&t, dim, n, precision, 1) != NB200_OK) return;
+    if (nb200_create(&t, dim, n, precision == 48 ? NB200_FP32 : precision, 1) != NB200_OK) return;
+    if (precision == 48) nb200_set_option(t, "fp32_positions", 48);
     for (int pass = 0; pass < 2; ++pass) {          // the small-N kernels, then the pre-pass + pair-symmetric ones
         nb200_set_option(t, "detect", pass);
         if (nb200_upload_aos(t, aos.data(), w * sizeof(double)) != NB200_OK) break;

@@ -315,6 +315,70 @@ def test_fp32_against_the_reference_on_unrounded_inputs(pkg, oracle, dim, med, p
     assert e64.max() <= TOL64
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("n", [300, 5000, 20000, 65536])
+def test_fp32_with_48_bit_positions_against_the_reference_on_unrounded_inputs(pkg, oracle, dim, n):
+    """Option fp32_positions = 48: FP32 pair arithmetic on positions held as float pairs (hi + lo).  Against the
+    reference on IDENTICAL unrounded double inputs in its own range (pos U[1,1e7], utils.h:113-115) the per-body
+    error must hold the FP32 contract's band -- max(1e-5, 6e-7 kappa) -- which the plain FP32 mode only holds on
+    float-quantised inputs; a duplicate and a pair under the cut-off included; then a few fused steps against the
+    FP64 mode (the finish kernel rewrites the lo rows every step)."""
+    gen = pkg.generators
+    b = gen.reference_range(n, dim, seed=300 + n)
+    b[17, :dim] = b[3, :dim]
+    b[101, :dim] = b[100, :dim] + 2e-6
+    idx = np.arange(n) if n <= 20000 else np.sort(np.random.default_rng(5).choice(n, 2000, replace=False))
+    ref = oracle.forces_targets(b, idx)
+    kappa = oracle.condition_targets(b, idx)
+    with pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as ctx:
+        ctx.set_option("fp32_positions", 48)
+        ctx.upload(b)
+        f = ctx.forces()
+        assert "[48-bit positions]" in ctx.plan and "cutoff=exact" in ctx.plan, ctx.plan
+        with pytest.raises(pkg.NB200Error):
+            ctx.set_option("fp32_positions", 24)        # fixed at upload
+    assert np.all(np.isfinite(f))
+    e = rel(pkg, f[idx], ref)
+    bound = pkg.fp32_error_bound(kappa)
+    assert np.all(e <= bound), f"worst {np.max(e / bound):.2f} x the bound (err {e.max():.3e})"
+    assert np.percentile(e, 99) <= 2e-6
+    # the plain FP32 mode on the same unrounded inputs is far outside that band (what the option is for)
+    e24 = rel(pkg, pkg.brute_force_cuda_n_body(b, pkg.NB200_FP32)[idx], ref)
+    if n >= 5000:
+        assert np.percentile(e24, 99) > 5 * np.percentile(e, 99)
+    # fused steps: the finish kernel rewrites hi AND lo rows; on a set that really moves (unit cube, unit-scale
+    # accelerations, unrounded doubles) the forces after the steps must match the oracle on the downloaded state
+    c = gen.uniform_cube(n, dim, seed=400 + n)
+    with pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as ctx:
+        ctx.set_option("fp32_positions", 48)
+        ctx.upload(c)
+        ctx.step(1e-5, 5)
+        state = c.copy()
+        ctx.download(state)
+        f2 = ctx.forces()
+    assert np.abs(state[:, :dim] - c[:, :dim]).max() > 1e-6          # the bodies moved by far more than a float ulp
+    e2 = rel(pkg, f2[idx], oracle.forces_targets(state, idx))
+    bound2 = pkg.fp32_error_bound(oracle.condition_targets(state, idx))
+    assert np.all(e2 <= bound2), f"after steps: worst {np.max(e2 / bound2):.2f} x the bound (err {e2.max():.3e})"
+    # against the FP64 mode over the same steps; 99.9th percentiles, because Poisson-uniform sets hold a few pairs so
+    # close that their five-step trajectories amplify any rounding difference
+    want = pkg.brute_force_cuda_simulate(c, 1e-5, 5, pkg.NB200_FP64)
+    diff = np.abs(state[:, :2 * dim] - want[:, :2 * dim]).max(axis=1)
+    assert np.percentile(diff, 99.9) <= 2e-6 * np.percentile(np.abs(want[:, :2 * dim]).max(axis=1), 99.9)
+
+
+def test_48_bit_positions_option_is_checked(pkg):
+    with pkg.NBodyCuda(3, 1000, pkg.NB200_FP64) as ctx:
+        with pytest.raises(pkg.NB200Error):
+            ctx.set_option("fp32_positions", 48)            # FP32 contexts only
+    with pkg.NBodyCuda(3, 1000, pkg.NB200_FP32) as ctx:
+        with pytest.raises(pkg.NB200Error):
+            ctx.set_option("fp32_positions", 32)
+        ctx.set_option("fp32_positions", 48)
+        with pytest.raises(pkg.NB200Error):
+            ctx.set_option("deterministic", 1)
+
+
 def test_fp32_full_population_error_on_the_device(pkg, oracle):
     """nb200_compare_forces: FP32-mode forces of ALL bodies against an FP64 context on the same
     float-quantised inputs (histogram by decade, maximum).  At N = 65536 the full CPU oracle is still

@@ -34,7 +34,7 @@ def test_adapter_fails_loudly_without_gpu():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dim", [2, 3])
-@pytest.mark.parametrize("precision", ["64", "32"])
+@pytest.mark.parametrize("precision", ["64", "32", "48"])
 def test_cpp_adapter_matches_oracle(dim, precision):
     if not os.path.exists(ADAPTER):
         pytest.skip("build/test_adapter not built")
