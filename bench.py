@@ -586,6 +586,12 @@ def run_product_arm(args) -> None:
         "peak_measured_source": "nb200_measure_fp32_peak: independent packed FFMA2 chains timed with CUDA events in this run",
         # ordered pass: 11 FMA-pipe lane-ops per interaction; pair-symmetric pass: 15 per pair of interactions
         "fma_pipe_lane_ops_per_interaction": 7.5 if "pair-symmetric" in plan else 11,
+        # what the pipe really did: executed lane-ops per interaction (FP32: 15 packed instructions per two pairs + the
+        # hand-over adds of the rotation = 7.7; FP64: 18 DP instructions per pair = 9) x interactions / pipe capacity --
+        # the figure ncu reports as pipe-active (profiles/), unlike `frac` not inflated by the 20-flop convention
+        "pipe_utilisation": round(value * 1e9 * ((7.7 if "pair-symmetric" in plan else 11) if prec == 32 else
+                                                 (9.0 if "pair-symmetric" in plan else 14.0))
+                                  / (sms * lanes * sm_max * 1e6 * world), 4),
         "traffic": traffic, "traffic_source": traffic_src,
         "hbm_algorithmic_bytes_per_step": n * (16 if prec == 32 else 32) + n * (2 * DIM * 8 * 2 + 8 + 3 * 8 * 2),
     }
