@@ -52,7 +52,7 @@ typedef struct nb200_ctx nb200_ctx;
  *             NB200_FP64, or option "fp32_positions" = 48 (below): the same FP32 pair arithmetic on positions kept as
  *             float PAIRS (hi + lo), differences taken as (hi_j - hi_i) + (lo_j - lo_i).  Then the band above holds
  *             against the reference on the UNROUNDED inputs (measured on the same 2^20 bodies: 4 above 1e-5, maximum
- *             2.3e-5) at 70 % of the FP32 throughput (2726 vs 3904 G interactions/s; FP64: 1706).  One GPU, pair-
+ *             2.3e-5) at 74 % of the FP32 throughput (2900 vs 3904 G interactions/s; FP64: 1706).  One GPU, pair-
  *             symmetric pass.  The reference's own -a 1 criterion (1 % per component, utils.h:170-219) is met by all. */
 #define NB200_FP64 64
 #define NB200_FP32 32
@@ -247,8 +247,9 @@ long long nb200_launch_count(const nb200_ctx* ctx);
  *                 NB200_ESTATE naming the peer and what was awaited, and the context refuses further work
  *   "fp32_positions"  24 (default) or 48, NB200_FP32 contexts on one GPU, set BEFORE the upload: 48 keeps every scaled
  *                 coordinate as two floats (the second row is written by the pack kernel and by the integrator every
- *                 step) so that the 24-bit quantisation of the positions no longer moves the near field; every pair takes
- *                 the exact cut-off (no pre-pass); excludes "deterministic"
+ *                 step) so that the 24-bit quantisation of the positions no longer moves the near field; the close-pair
+ *                 pre-pass runs on the hi parts with cells widened by their largest difference error; excludes
+ *                 "deterministic"
  *   "trace"       1 = append a CUDA-event timeline of shard 0 to nb200_plan() after nb200_step.  Independently of it every
  *                 entry point that touches the device opens an NVTX range of its own name (visible in Nsight Systems;
  *                 a no-op without a tool attached)

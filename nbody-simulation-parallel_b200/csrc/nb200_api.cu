@@ -506,7 +506,6 @@ struct Plan {
 // pays from N ~ 50000: measured at N = 65536, FP32: 1.275 vs 1.296 ms/step in 3D, 0.944 vs 1.002 in 2D; at 32768 (3D) it
 // loses, 0.432 vs 0.351 (profiles/r02/small_n.md).
 bool use_detect(const nb200_ctx* ctx) {
-    if (ctx->opt_pos48) return false;        // the pre-pass sees the hi parts only: every pair takes the exact cut-off
     if (ctx->opt_detect >= 0) return ctx->opt_detect != 0;
     return ctx->n >= 49152u;
 }
@@ -606,7 +605,11 @@ int launch_detect(nb200_ctx* ctx, Shard& s, double cutoff, int cur) {
     g.mask = s.grid_cap - 1;
     // cell edge >= sqrt(cutoff) * 1.001; with no cut-off only exact duplicates matter: any tiny cell does,
     // but keep cell indices far inside the int64 range
-    const double h = cs > 0.0 ? sqrt(cs) * 1.001 : ldexp(ctx->xmax * ctx->pos_scale, -40);
+    // 48-bit positions: the grid is built on the hi parts, whose pair differences are off by up to 2^-24 per coordinate
+    // (|x'| <= 1 at upload): cells twice that much wider keep "no other body in the 3^D cells around" a proof that no TRUE distance is
+    // under the cut-off
+    const double h = (cs > 0.0 ? sqrt(cs) * 1.001 : ldexp(ctx->xmax * ctx->pos_scale, -40)) +
+                     (ctx->opt_pos48 ? ldexp(std::max(1.0, ctx->xmax * ctx->pos_scale), -23) : 0.0);   // 2x: bodies may leave the uploaded range
     g.inv_h = 1.0 / h;
     // one memset (keys = empty, counts = -1), then insert -> query -> force pass chained by programmatic dependent launch
     CK(cudaMemsetAsync(s.grid_keys, 0xFF, (size_t)s.grid_cap * (sizeof(unsigned long long) + sizeof(unsigned)), s.compute));

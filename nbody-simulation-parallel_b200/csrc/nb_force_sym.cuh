@@ -538,7 +538,8 @@ __device__ __forceinline__ void nb_tile_f64_sym_rot(const double* __restrict__ s
 
 // ALGO: 0 = shared-memory transpose of the reaction sums, 1 = register rotation, 2 (FP32) = rotation, decoupled
 //       HL (FP32 rotation, general masses): 48-bit positions -- a stage holds the D + 1 hi planes of a tile followed by
-//       its D lo planes (two bulk copies on one barrier), the exact cut-off is applied to every pair
+//       its D lo planes (two bulk copies on one barrier); the pre-pass, which sees the hi parts, widens its cells by the
+//       largest hi-part difference error so that its flags stay conservative
 template <int D, bool F64, int TI, int BLOCK, int ALGO = 0, bool EQM = false, bool HL = false>
 __global__ void __launch_bounds__(BLOCK, nb_sym_min_blocks(F64, TI, BLOCK, D, EQM))
 nb_force_sym_kernel(const NbSymParams P) {
@@ -735,13 +736,17 @@ nb_force_sym_kernel(const NbSymParams P) {
                         if (exact_tile) nb_tile_f32_sym<D, TI, NB_EXACT>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
                         else nb_tile_f32_sym<D, TI, NB_PLAIN>(fstage, cutoff_f, npos, mif, a, scr, fwout, lane);
                     } else {
-                        if constexpr (HL) nb_tile_f32_sym_rot<D, TI, NB_EXACT, true, false, true>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1, tlo);
-                        else if (exact_tile) nb_tile_f32_sym_rot<D, TI, NB_EXACT, ALGO == 2, EQM>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1);
+                        if constexpr (HL) {
+                            if (exact_tile) nb_tile_f32_sym_rot<D, TI, NB_EXACT, true, false, true>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1, tlo);
+                            else nb_tile_f32_sym_rot<D, TI, NB_PLAIN, true, false, true>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1, tlo);
+                        } else if (exact_tile) nb_tile_f32_sym_rot<D, TI, NB_EXACT, ALGO == 2, EQM>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1);
                         else nb_tile_f32_sym_rot<D, TI, NB_PLAIN, ALGO == 2, EQM>(fstage, cutoff_f, npos, mif, a, fwout, lane, h0, h1);
                     }
                 } else {
-                    if constexpr (HL) nb_tile_f32<D, TI, 1, NB_EXACT, 1, false, true>(fstage, 0, cutoff_f, npos, a, tlo);
-                    else if (exact_tile) nb_tile_f32<D, TI, 1, NB_EXACT, 1, EQM>(fstage, 0, cutoff_f, npos, a);
+                    if constexpr (HL) {
+                        if (exact_tile) nb_tile_f32<D, TI, 1, NB_EXACT, 1, false, true>(fstage, 0, cutoff_f, npos, a, tlo);
+                        else nb_tile_f32<D, TI, 1, NB_PLAIN, 1, false, true>(fstage, 0, cutoff_f, npos, a, tlo);
+                    } else if (exact_tile) nb_tile_f32<D, TI, 1, NB_EXACT, 1, EQM>(fstage, 0, cutoff_f, npos, a);
                     else nb_tile_f32<D, TI, 1, NB_PLAIN, 1, EQM>(fstage, 0, cutoff_f, npos, a);
                 }
 #pragma unroll

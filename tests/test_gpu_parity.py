@@ -316,7 +316,7 @@ def test_fp32_against_the_reference_on_unrounded_inputs(pkg, oracle, dim, med, p
 
 
 @pytest.mark.parametrize("dim", [2, 3])
-@pytest.mark.parametrize("n", [300, 5000, 20000, 65536])
+@pytest.mark.parametrize("n", [300, 5000, 20000, 65536, 100000])
 def test_fp32_with_48_bit_positions_against_the_reference_on_unrounded_inputs(pkg, oracle, dim, n):
     """Option fp32_positions = 48: FP32 pair arithmetic on positions held as float pairs (hi + lo).  Against the
     reference on IDENTICAL unrounded double inputs in its own range (pos U[1,1e7], utils.h:113-115) the per-body
@@ -327,14 +327,22 @@ def test_fp32_with_48_bit_positions_against_the_reference_on_unrounded_inputs(pk
     b = gen.reference_range(n, dim, seed=300 + n)
     b[17, :dim] = b[3, :dim]
     b[101, :dim] = b[100, :dim] + 2e-6
-    idx = np.arange(n) if n <= 20000 else np.sort(np.random.default_rng(5).choice(n, 2000, replace=False))
+    # a pair UNDER the cut-off whose float (hi) parts differ by one ulp in every coordinate: the two bodies straddle a
+    # rounding boundary of the float grid (ulp 0.5 at 5e6), 4e-6 apart -- dropped by the reference, and the pre-pass,
+    # which sees the hi parts only, must still send it through the exact flavour
+    edge = 5.0e6 + 0.25
+    b[200, :dim] = edge + 2e-6
+    b[201, :dim] = edge - 2e-6
+    assert np.all(b[200, :dim].astype(np.float32) != b[201, :dim].astype(np.float32))
+    idx = np.arange(n) if n <= 20000 else np.sort(np.r_[np.random.default_rng(5).choice(n, 2000, replace=False), [3, 17, 100, 101, 200, 201]])
+    idx = np.unique(idx)
     ref = oracle.forces_targets(b, idx)
     kappa = oracle.condition_targets(b, idx)
     with pkg.NBodyCuda(dim, n, pkg.NB200_FP32) as ctx:
         ctx.set_option("fp32_positions", 48)
         ctx.upload(b)
         f = ctx.forces()
-        assert "[48-bit positions]" in ctx.plan and "cutoff=exact" in ctx.plan, ctx.plan
+        assert "[48-bit positions]" in ctx.plan and ("cutoff=exact" in ctx.plan) == (n < 49152), ctx.plan
         with pytest.raises(pkg.NB200Error):
             ctx.set_option("fp32_positions", 24)        # fixed at upload
     assert np.all(np.isfinite(f))
