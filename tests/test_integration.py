@@ -4,6 +4,7 @@ import csv
 import glob
 import os
 import subprocess
+import sys
 
 import pytest
 
@@ -137,3 +138,19 @@ def test_steps_and_dt_flags_select_the_fused_step(tmp_path, dim=3):
     rows = [row for f in glob.glob(os.path.join(tmp_path, "results", "*.csv")) for row in csv.DictReader(open(f))]
     assert [row["Method"] for row in rows] == ["BruteForce_CUDA", "BruteForce_CUDA_Steps"]
     assert float(rows[1]["Time(s)"]) > 0 and "25 steps of dt=0.0001" in r.stdout
+
+
+def test_sweep_rows_aggregate_into_the_notebook_layout(tmp_path):
+    """integration/aggregate_rows.py: rows of the patched suite's CSVs -> `Bodies,Method,Dimension,Average Runtime (s)`
+    (the reference's analysis/aggregated_results.csv), duplicates of one (N, D) averaged."""
+    src = tmp_path / "rows.csv"
+    src.write_text("Method,Bodies,Dimension,Time(s),Accuracy(%),Precision\n"
+                   "BruteForce_CUDA,1000,2,0.0002,,64\nBruteForce_CUDA,1000,2,0.0004,100.00,64\n"
+                   "BruteForce_CUDA,1000,3,0.0005,,64\nBruteForce_CUDA,10000,2,0.003,,64\n")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "aggregate_rows.py"), str(src)],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    rows = list(csv.reader(r.stdout.splitlines()))
+    assert rows[0] == ["Bodies", "Method", "Dimension", "Average Runtime (s)"]
+    assert rows[1][:3] == ["1000", "BruteForce_CUDA", "2"] and abs(float(rows[1][3]) - 0.0003) < 1e-12
+    assert rows[2][:3] == ["10000", "BruteForce_CUDA", "2"] and rows[3][:3] == ["1000", "BruteForce_CUDA", "3"]
