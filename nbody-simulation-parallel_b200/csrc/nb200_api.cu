@@ -191,7 +191,8 @@ struct Shard {
 constexpr int kMaxWorldP2P = NB_MAX_PEERS + 1;
 constexpr int kSymMaxSlots = kMaxWorldP2P / 2;      // senders of reaction sums per rank: floor(world / 2)
 // One allocation per shard (one IPC handle): 4 * kMaxWorldP2P flag words (step, upload epoch, reaction-sum pass, upload
-// ready; one per writer rank each), the per-rank bounds table of a shard-local upload (2 words per rank), then the
+// ready; one per writer rank each), the per-rank bounds table of a shard-local upload (3 words per rank: max |x|, max |m|,
+// min |m|), then the
 // receive slots of the pair-symmetric pass.
 constexpr size_t kFlagsBytes = 512;
 constexpr int kBoundsTableWord = 4 * (NB_MAX_PEERS + 1);          // 3 words per rank: 32 + 24 <= 64 words
