@@ -16,10 +16,13 @@
 // A thread keeps TI targets in registers ("a" side, summed per tile into FP64 exactly like
 // nb_force_kernel); the reaction on the streamed sources ("b" side) is produced per lane for four
 // sources (FP64: two) per iteration and reduced
-//   lane partials -> warp  : a 32 x 12-word shared-memory transpose (6 STS.64, 16 LDS, 16 FADD)
+//   lane partials -> warp  : ALGO 1/2 (default): the sums of a group of sources travel through the warp in registers,
+//                            one lane per step (nb_tile_f32_sym_rot / nb_tile_f64_sym_rot, 12 SHFL per step);
+//                            ALGO 0 (round 1): a 32 x 12-word shared-memory transpose (6 STS.64, 16 LDS, 16 FADD)
 //   warp sums     -> CTA   : per-warp [D][256] tile buffers, summed by the CTA after the tile
 //   CTA tile sums -> global: one FP64 atomicAdd per (source, component) per tile, into an
 //                            accumulator array indexed by GLOBAL body (any body can receive)
+// Flavours: EQM (equal-mass systems: the masses leave the chain), HL (FP32 on 48-bit positions: float pairs hi + lo).
 // The integrator/forces epilogue cannot be fused here (an i-tile also receives "b" sums from the
 // units of other i-tiles and, across ranks, from other GPUs: nb_sym_push_kernel), so
 // nb_finish_kernel runs after the pass.
